@@ -1,0 +1,69 @@
+"""ctypes binding of include/dvt_b200.h.  Fails loudly when the shared object is missing or a call errors."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_uint, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdvt_b200.so")
+
+
+class DvtError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol of include/dvt_b200.h (tests/test_abi.py checks this)
+SIGNATURES = {
+    "dvt_version": (c_int, []),
+    "dvt_last_error": (c_char_p, []),
+    "dvt_device_error": (c_int, [POINTER(c_uint)]),
+    "dvt_set_debug_impl": (c_int, [c_int]),
+    "dvt_gemm_tn": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                            c_int, c_int, c_int, c_void_p]),
+    "dvt_gemm_tn_residual": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_int, c_void_p]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise DvtError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().dvt_last_error().decode("utf-8", "replace")
+        raise DvtError(f"{what} failed (code {rc}): {msg}")
+
+
+def device_error() -> int:
+    code = c_uint(0)
+    check(lib().dvt_device_error(ctypes.byref(code)), "dvt_device_error")
+    return code.value
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+DT_BF16, DT_F32 = 0, 1
