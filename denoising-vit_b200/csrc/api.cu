@@ -5,6 +5,17 @@
 #include "gemm.cuh"
 
 namespace dvt {
+struct Vit;
+int vit_create(Vit** out, int embed, int depth, int heads, int patch, int mlp_hidden, int swiglu, int layerscale,
+               int prefix, float ln_eps);
+void vit_destroy(Vit* v);
+int vit_load(Vit* v, const char* name, const float* src, size_t numel);
+int vit_reserve(Vit* v, size_t tokens, size_t patches);
+int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int stride, const float* pos_patch,
+                const float* prefix_rows, int layer_index, int apply_norm, float* out, int out_all_tokens,
+                cudaStream_t stream, int impl);
+int vit_patch(const Vit* v);
+int vit_prefix(const Vit* v);
 const char* last_error();
 extern int g_debug_impl_override;
 int g_debug_impl_override = -1;
@@ -72,6 +83,56 @@ int dvt_gemm_tn_residual(const void* A, int lda, const void* B, int ldb, int dty
   GemmShape s{M, N, K, 1};
   return launch_gemm_tn(A, lda, B, ldb, dtype == DVT_DTYPE_BF16 ? TMAP_BF16 : TMAP_F32, s, e,
                         reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+
+int dvt_layernorm(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int y_dtype,
+                  int rows, int C, float eps, int in_group, int skip, void* stream) {
+  DVT_REQUIRE(x && gamma && beta && y, "dvt_layernorm: null pointer");
+  DVT_REQUIRE(in_group >= 1 && skip >= 0 && skip < in_group + (in_group == 1), "dvt_layernorm: bad in_group/skip");
+  return launch_layernorm(x, ldx, gamma, beta, y, ldy, y_dtype == DVT_DTYPE_BF16, rows, C, eps, in_group, skip,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dvt_attention_fwd(const void* qkv_bf16, void* out_bf16, int B, int N, int heads, void* stream) {
+  DVT_REQUIRE(qkv_bf16 && out_bf16, "dvt_attention_fwd: null pointer");
+  int impl = eff_impl();
+  if (impl < 0) impl = default_gemm_impl();
+  return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                          B, N, heads, reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int dvt_im2col(const void* x, int x_dtype, void* out_bf16, int B, int H, int W, int P, int S, void* stream) {
+  DVT_REQUIRE(x && out_bf16 && P > 0 && S > 0 && H >= P && W >= P, "dvt_im2col: bad arguments");
+  const int h = (H - P) / S + 1, w = (W - P) / S + 1, Kp = (3 * P * P + 7) / 8 * 8;
+  return launch_im2col(x, x_dtype == DVT_DTYPE_BF16, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, H, W, P, S, h, w, Kp,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dvt_vit_create(dvt_vit_t** out, int embed, int depth, int heads, int patch, int mlp_hidden, int swiglu,
+                   int layerscale, int prefix_tokens, float ln_eps) {
+  DVT_REQUIRE(out, "dvt_vit_create: null out");
+  return vit_create(reinterpret_cast<Vit**>(out), embed, depth, heads, patch, mlp_hidden, swiglu, layerscale,
+                    prefix_tokens, ln_eps);
+}
+void dvt_vit_destroy(dvt_vit_t* h) { vit_destroy(reinterpret_cast<Vit*>(h)); }
+int dvt_vit_load(dvt_vit_t* h, const char* timm_key, const float* src, size_t numel) {
+  DVT_REQUIRE(h && timm_key && src, "dvt_vit_load: null argument");
+  return vit_load(reinterpret_cast<Vit*>(h), timm_key, src, numel);
+}
+int dvt_vit_reserve(dvt_vit_t* h, int max_batch, int H, int W, int stride) {
+  DVT_REQUIRE(h && max_batch > 0 && stride > 0, "dvt_vit_reserve: bad arguments");
+  Vit* v = reinterpret_cast<Vit*>(h);
+  const int P = vit_patch(v);
+  DVT_REQUIRE(H >= P && W >= P, "dvt_vit_reserve: image smaller than a patch");
+  const size_t np = (size_t)((H - P) / stride + 1) * ((W - P) / stride + 1);
+  return vit_reserve(v, (size_t)max_batch * (np + vit_prefix(v)), (size_t)max_batch * np);
+}
+int dvt_vit_forward(dvt_vit_t* h, const void* x, int x_dtype, int B, int H, int W, int stride,
+                    const float* pos_patch, const float* prefix_rows, int layer_index, int norm, float* out,
+                    int all_tokens, void* stream) {
+  DVT_REQUIRE(h, "dvt_vit_forward: null handle");
+  return vit_forward(reinterpret_cast<Vit*>(h), x, x_dtype == DVT_DTYPE_BF16, B, H, W, stride, pos_patch, prefix_rows,
+                     layer_index, norm, out, all_tokens, reinterpret_cast<cudaStream_t>(stream), eff_impl());
 }
 
 }  // extern "C"

@@ -1,0 +1,356 @@
+// Multi-head self-attention forward for head_dim 64 on tcgen05 tensor cores (flash-style, O(N) memory).
+//
+//   qkv  : bf16 [B, N, 3*C]  (the QKV projection output, C = heads*64; q at col h*64, k at C + h*64, v at 2C + h*64)
+//   out  : bf16 [B, N, C]    (col = h*64 + d; directly the A operand of the out-projection GEMM)
+//
+// One CTA per (query tile of 128 rows, head, image), 6 warps:
+//   warp 0     TMA producer: Q tile once, then K/V tiles (128 keys x 64) through a 2-deep ring (3-D tensor map
+//              over [3C, N, B]; keys past N are zero-filled)
+//   warp 1     MMA issuer: S = Q.K^T (M128 N128 K16 x4, K-major operands) into one of two TMEM buffers;
+//              O_j = P_j.V_j (M128 N64 K16 x8; P from smem K-major, V straight from its TMA tile as an MN-major
+//              operand) into one of two TMEM buffers
+//   warps 2-5  softmax: one thread per query row (TMEM lane = row): tcgen05.ld S, online max / exp2 / sum in
+//              fp32, P -> bf16 into 128B-swizzled smem, O accumulated in registers (acc = (acc + O_{j-1}) * alpha)
+// Reference semantics: timm Attention.forward, restated at evaluation/vitdet/vision_transformer.py:73-91
+// (scale d^-0.5, no mask, softmax over keys).
+#include "common.cuh"
+
+namespace dvt {
+
+namespace {
+
+constexpr int ATT_D = 64;
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BK = 128;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+// smem layout (offsets from a 1024-aligned base)
+constexpr int ATT_OFF_Q = 0;
+constexpr int ATT_OFF_K = ATT_OFF_Q + ATT_TILE_BYTES;          // 2 stages
+constexpr int ATT_OFF_V = ATT_OFF_K + 2 * ATT_TILE_BYTES;      // 2 stages
+constexpr int ATT_OFF_P = ATT_OFF_V + 2 * ATT_TILE_BYTES;      // 2 buffers x 2 k-atoms x 16 KB
+constexpr int ATT_OFF_BAR = ATT_OFF_P + 4 * ATT_TILE_BYTES;
+constexpr int ATT_NUM_BARS = 1 + 2 + 2 + 2 + 2 + 2 + 2 + 2 + 2;
+constexpr int ATT_OFF_TMEM = ATT_OFF_BAR + ATT_NUM_BARS * 8;
+constexpr int ATT_SMEM_TOTAL = ATT_OFF_TMEM + 16 + 1024;
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+constexpr uint32_t ATT_TMEM_COLS = 512;
+constexpr uint32_t ATT_TM_S = 0, ATT_TM_O = 256;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int C,
+                    float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + ATT_OFF_Q;
+  uint8_t* sK = smem + ATT_OFF_K;
+  uint8_t* sV = smem + ATT_OFF_V;
+  uint8_t* sP = smem + ATT_OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 11;
+  uint64_t* p_full = bars + 13;
+  uint64_t* o_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ATT_OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int T = (N + ATT_BK - 1) / ATT_BK;  // key tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tm_qkv, q_full, head * ATT_D, q0, b);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1, 10);
+        mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+        tma_load_3d(sK + st * ATT_TILE_BYTES, &tm_qkv, &k_full[st], C + head * ATT_D, j * ATT_BK, b);
+        mbar_wait(&v_empty[st], ph ^ 1, 11);
+        mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
+        tma_load_3d(sV + st * ATT_TILE_BYTES, &tm_qkv, &v_full[st], 2 * C + head * ATT_D, j * ATT_BK, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(1, 128, 128, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = make_idesc(1, 128, 64, 0, 1);   // P (K-major) x V (MN-major)
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[st], ph, 12);
+        mbar_wait(&s_empty[st], ph ^ 1, 13);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(smem_u32(sQ), 0, 1024, 2);
+        const uint64_t db = make_smem_desc(smem_u32(sK + st * ATT_TILE_BYTES), 0, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + ATT_TM_S + st * 128, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0, 14);
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_qk(j + 1);
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&v_full[st], ph, 15);
+        mbar_wait(&p_full[st], ph, 16);
+        tc_fence_after();
+        // P buffer st: two K-atoms (keys 0-63, 64-127), each a [128 x 128B] swizzled tile
+        const uint32_t p_base = smem_u32(sP + st * 2 * ATT_TILE_BYTES);
+        const uint32_t v_base = smem_u32(sV + st * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = make_smem_desc(p_base + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 0, 1024, 2);
+          // V tile rows are keys (K dim), 128 B each: 16 keys per MMA = 2048 B; 8-row groups 1024 B apart
+          const uint64_t db = make_smem_desc(v_base + k * 2048, 0, 1024, 2);
+          umma_f16(tmem_base + ATT_TM_O + st * 64, da, db, idesc_o, k > 0);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(&o_full[st]);
+      }
+    }
+  } else {
+    // ===================== softmax / accumulate / store =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float acc[ATT_D];
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
+    float m_run = -INFINITY;  // running max of s * scale_log2e
+    float l_run = 0.f;
+
+    for (int j = 0; j < T; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&s_full[st], ph, 17);
+      tc_fence_after();
+      // ---- pass 1: row max over this tile (TMEM is re-read in pass 2: cheaper than 128 live registers) ----
+      const int kbase = j * ATT_BK;
+      const bool partial = kbase + ATT_BK > N;  // only the last tile can hold keys >= N
+      float m_tile = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sreg[32];
+        tmem_ld_32x32(lane_addr + ATT_TM_S + st * 128 + c * 32, sreg);
+        tmem_ld_wait();
+        if (partial) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i < N) m_tile = fmaxf(m_tile, __uint_as_float(sreg[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sreg[i]));
+        }
+      }
+      m_tile *= scale_log2e;                      // scale > 0: max commutes with the scaling
+      const float m_new = fmaxf(m_run, m_tile);  // finite: every tile has at least one valid key
+      const float alpha = ex2(m_run - m_new);     // 0 on the first tile (m_run = -inf)
+      // ---- pass 2: p = exp2(s*scale - m_new), row sum, bf16 pack, swizzled store ----
+      float l_tile = 0.f;
+      uint8_t* pbuf = sP + st * 2 * ATT_TILE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sreg[32];
+        tmem_ld_32x32(lane_addr + ATT_TM_S + st * 128 + c * 32, sreg);
+        tmem_ld_wait();
+        if (c == 3) {
+          tc_fence_before();
+          mbar_arrive(&s_empty[st]);  // S buffer may now be overwritten by QK of tile j+2
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(sreg[2 * i]), scale_log2e, -m_new));
+          float p1 = ex2(fmaf(__uint_as_float(sreg[2 * i + 1]), scale_log2e, -m_new));
+          if (partial) {
+            if (kbase + c * 32 + 2 * i >= N) p0 = 0.f;
+            if (kbase + c * 32 + 2 * i + 1 >= N) p1 = 0.f;
+          }
+          l_tile += p0 + p1;
+          packed[i] = pack_bf16x2(p0, p1);
+        }
+        // keys [c*32, c*32+32) -> k-atom (c >> 1), 16B chunks ((c & 1) * 4 + q), q = 0..3
+        uint8_t* atom = pbuf + (c >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
+          *reinterpret_cast<uint4*>(atom + chunk * 16) =
+              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      fence_async_smem();  // generic-proxy writes of P -> visible to tcgen05.mma
+      mbar_arrive(&p_full[st]);
+      // ---- fold in the previous tile's O, rescale to the new max ----
+      if (j > 0) {
+        const int pst = (j - 1) & 1;
+        const uint32_t pph = ((j - 1) >> 1) & 1;
+        mbar_wait(&o_full[pst], pph, 18);
+        tc_fence_after();
+        uint32_t o[2][32];
+        tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64, o[0]);
+        tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64 + 32, o[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int d = 0; d < ATT_D; ++d) acc[d] = (acc[d] + __uint_as_float(o[d >> 5][d & 31])) * alpha;
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+    }
+    // last tile's O
+    {
+      const int pst = (T - 1) & 1;
+      const uint32_t pph = ((T - 1) >> 1) & 1;
+      mbar_wait(&o_full[pst], pph, 19);
+      tc_fence_after();
+      uint32_t o[2][32];
+      tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64, o[0]);
+      tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64 + 32, o[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      const float inv = 1.0f / l_run;
+      const int q = q0 + row;
+      if (q < N) {
+        __nv_bfloat16* dst = out + ((size_t)b * N + q) * C + head * ATT_D;
+#pragma unroll
+        for (int d8 = 0; d8 < 8; ++d8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int d = d8 * 8 + 2 * i;
+            const float a0 = (acc[d] + __uint_as_float(o[d >> 5][d & 31])) * inv;
+            const float a1 = (acc[d + 1] + __uint_as_float(o[(d + 1) >> 5][(d + 1) & 31])) * inv;
+            w[i] = pack_bf16x2(a0, a1);
+          }
+          *reinterpret_cast<uint4*>(dst + d8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// SIMT debug attention: one warp per (query, head, image); three passes over the keys.
+// ----------------------------------------------------------------------------------------------------
+__global__ void attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int N,
+                                      int C, float scale) {
+  extern __shared__ float sc[];  // [N] scores
+  const int q = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x;
+  const __nv_bfloat16* base = qkv + (size_t)b * N * 3 * C;
+  const __nv_bfloat16* qp = base + (size_t)q * 3 * C + head * ATT_D;
+  float qv[ATT_D];
+#pragma unroll
+  for (int d = 0; d < ATT_D; ++d) qv[d] = __bfloat162float(qp[d]);
+  float mx = -INFINITY;
+  for (int k = lane; k < N; k += 32) {
+    const __nv_bfloat16* kp = base + (size_t)k * 3 * C + C + head * ATT_D;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) s = fmaf(qv[d], __bfloat162float(kp[d]), s);
+    s *= scale;
+    sc[k] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int k = lane; k < N; k += 32) {
+    const float p = __expf(sc[k] - mx);
+    sc[k] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+  for (int k = 0; k < N; ++k) {
+    const __nv_bfloat16* vp = base + (size_t)k * 3 * C + 2 * C + head * ATT_D;
+    const float p = sc[k];
+    o0 = fmaf(p, __bfloat162float(vp[2 * lane]), o0);
+    o1 = fmaf(p, __bfloat162float(vp[2 * lane + 1]), o1);
+  }
+  __nv_bfloat16* dst = out + ((size_t)b * N + q) * C + head * ATT_D;
+  *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16x2(o0 / sum, o1 / sum);
+}
+
+}  // namespace
+
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t stream,
+                     int impl) {
+  const int C = heads * ATT_D;
+  DVT_REQUIRE(B > 0 && N > 0 && heads > 0, "attention: bad shape B=%d N=%d heads=%d", B, N, heads);
+  const float scale = 0.125f;  // 64^-0.5
+  if (impl == 1) {
+    DVT_REQUIRE(N <= 12000, "attention (simt debug): N=%d too large", N);
+    dim3 grid(N, heads, B);
+    attention_simt_kernel<<<grid, 32, N * sizeof(float), stream>>>(qkv, out, N, C, scale);
+    DVT_CUDA_OK(cudaGetLastError());
+    return DVT_OK;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    attr_set = true;
+  }
+  CUtensorMap tm;
+  int rc = make_tmap_3d(&tm, qkv, TMAP_BF16, (uint64_t)3 * C, (uint64_t)N, (uint64_t)B, (uint64_t)3 * C * 2,
+                        (uint64_t)N * 3 * C * 2, ATT_D, ATT_BK);
+  if (rc) return rc;
+  dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
+  attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(tm, out, N, C, scale * 1.4426950408889634f);
+  DVT_CUDA_OK(cudaGetLastError());
+  return DVT_OK;
+}
+
+}  // namespace dvt

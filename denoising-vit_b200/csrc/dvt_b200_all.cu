@@ -1,4 +1,7 @@
 // Unity translation unit: one device link unit (no -rdc), one shared object.
 #include "runtime.cu"
 #include "gemm.cu"
+#include "vit_kernels.cu"
+#include "attention.cu"
+#include "vit.cu"
 #include "api.cu"

@@ -1,0 +1,181 @@
+// Bandwidth-bound helpers of the frozen-ViT forward (HP-1): LayerNorm (warp per row, float4 loads, shuffle
+// reductions), im2col for the patch-embed conv with arbitrary stride, prefix-token rows, SwiGLU gate, casts.
+// Reference semantics: timm 1.0.7 VisionTransformer reached from dvt/models/vit_wrapper.py:136-143
+// (patch_embed conv with the stride override of vit_wrapper.py:78-79; LayerNorm eps 1e-6; final norm + prefix
+// strip + NHWC store replaces the NCHW round trip of main_img_denoising.py:317-323).
+#include "common.cuh"
+
+namespace dvt {
+
+// ----------------------------------------------------------------------------------------------------
+// LayerNorm: y = (x - mean) / sqrt(var + eps) * gamma + beta, rows of C fp32 (C % 4 == 0, C <= 2048).
+// Row mapping: input row r = g * in_group + t (t < in_group).  Rows with t < skip are dropped; output row =
+// g * (in_group - skip) + (t - skip).  (skip = number of prefix tokens when writing the patch-only NHWC map.)
+// ----------------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, OutT* __restrict__ y, int ldy, int rows, int C,
+                                 float eps, int in_group, int skip) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  int out_row = warp;
+  if (skip > 0) {
+    const int g = warp / in_group, t = warp - g * in_group;
+    if (t < skip) return;
+    out_row = g * (in_group - skip) + (t - skip);
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * ldx);
+  const int nvec = C >> 2;
+  float4 v[16];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = __ldg(xr + idx);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(OutT) == 2) {
+        uint2 p;
+        p.x = pack_bf16x2(o.x, o.y);
+        p.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + (size_t)out_row * ldy + idx * 4) = p;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)out_row * ldy + idx * 4) = o;
+      }
+    }
+  }
+}
+
+int launch_layernorm(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, bool out_bf16,
+                     int rows, int C, float eps, int in_group, int skip, cudaStream_t stream) {
+  DVT_REQUIRE(C % 4 == 0 && C <= 2048 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: C=%d ldx=%d ldy=%d unsupported", C,
+              ldx, ldy);
+  if (rows <= 0) return DVT_OK;
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  if (out_bf16)
+    layernorm_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, rows,
+                                                                     C, eps, in_group > 0 ? in_group : 1, skip);
+  else
+    layernorm_kernel<float><<<blocks, threads, 0, stream>>>(x, ldx, gamma, beta, (float*)y, ldy, rows, C, eps,
+                                                            in_group > 0 ? in_group : 1, skip);
+  DVT_CUDA_OK(cudaGetLastError());
+  return DVT_OK;
+}
+
+// Same row mapping without normalisation (norm=False in get_intermediate_layers): plain strided copy.
+__global__ void strip_copy_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int rows, int C,
+                                  int in_group, int skip) {
+  const int row = blockIdx.x;
+  const int g = row / in_group, t = row - g * in_group;
+  if (t < skip) return;
+  const int out_row = g * (in_group - skip) + (t - skip);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) y[(size_t)out_row * ldy + c] = x[(size_t)row * ldx + c];
+}
+
+// ----------------------------------------------------------------------------------------------------
+// im2col for Conv2d(3 -> C, kernel P, stride S): x [B, 3, H, W] -> patches bf16 [B*h*w, Kp], column index
+// c*P*P + i*P + j (the flattening of the conv weight [C, 3, P, P]); columns >= 3*P*P are zero.
+// ----------------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void im2col_kernel(const InT* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W, int P,
+                              int S, int h, int w, int Kp) {
+  const size_t total = (size_t)B * h * w * Kp;
+  const int K = 3 * P * P;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(e % Kp);
+    const size_t row = e / Kp;
+    float v = 0.f;
+    if (col < K) {
+      const int c = col / (P * P);
+      const int ij = col - c * P * P;
+      const int i = ij / P, j = ij - i * P;
+      const int pw = (int)(row % w);
+      const int ph = (int)((row / w) % h);
+      const int b = (int)(row / ((size_t)w * h));
+      const size_t src = (((size_t)b * 3 + c) * H + (size_t)ph * S + i) * W + (size_t)pw * S + j;
+      if constexpr (sizeof(InT) == 2) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[src]);
+      else v = reinterpret_cast<const float*>(x)[src];
+    }
+    out[e] = __float2bfloat16_rn(v);
+  }
+}
+
+int launch_im2col(const void* x, bool x_bf16, __nv_bfloat16* out, int B, int H, int W, int P, int S, int h, int w,
+                  int Kp, cudaStream_t stream) {
+  const size_t total = (size_t)B * h * w * Kp;
+  if (total == 0) return DVT_OK;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < (size_t)num_sms() * 16 ? (total + threads - 1) / threads
+                                                                                     : (size_t)num_sms() * 16);
+  if (x_bf16)
+    im2col_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>((const __nv_bfloat16*)x, out, B, H, W, P, S, h, w, Kp);
+  else
+    im2col_kernel<float><<<blocks, threads, 0, stream>>>((const float*)x, out, B, H, W, P, S, h, w, Kp);
+  DVT_CUDA_OK(cudaGetLastError());
+  return DVT_OK;
+}
+
+// prefix rows (cls [+pos] and register tokens), precomputed as [prefix, C]; broadcast to every image of the batch
+__global__ void prefix_rows_kernel(const float* __restrict__ prefix_rows, float* __restrict__ x, int B, int prefix,
+                                   int ntok, int C) {
+  const int b = blockIdx.x / prefix, p = blockIdx.x % prefix;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    x[((size_t)b * ntok + p) * C + c] = prefix_rows[(size_t)p * C + c];
+}
+
+// SwiGLU (timm SwiGLUPacked, gate_last=False): out[m, j] = silu(h[m, j]) * h[m, j + Hh], h bf16 [M, 2*Hh]
+__global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ hin, __nv_bfloat16* __restrict__ out, size_t M, int Hh) {
+  const size_t total = M * Hh;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = e / Hh;
+    const int j = (int)(e - m * Hh);
+    const float a = __bfloat162float(hin[m * 2 * Hh + j]);
+    const float b = __bfloat162float(hin[m * 2 * Hh + Hh + j]);
+    out[e] = __float2bfloat16_rn(a / (1.f + __expf(-a)) * b);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+    out[e] = __float2bfloat16_rn(in[e]);
+}
+
+// conv weight [C, 3*P*P] fp32 -> bf16 [C, Kp] zero padded
+__global__ void pad_cast_rows_kernel(const float* __restrict__ in, int K, __nv_bfloat16* __restrict__ out, int Kp,
+                                     size_t rows) {
+  const size_t total = rows * Kp;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / Kp;
+    const int c = (int)(e - r * Kp);
+    out[e] = __float2bfloat16_rn(c < K ? in[r * K + c] : 0.f);
+  }
+}
+
+}  // namespace dvt

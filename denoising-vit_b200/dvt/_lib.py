@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_uint, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdvt_b200.so")
@@ -25,6 +25,16 @@ SIGNATURES = {
                             c_int, c_int, c_int, c_void_p]),
     "dvt_gemm_tn_residual": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p, c_int, c_void_p]),
+    "dvt_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
+                              c_int, c_void_p]),
+    "dvt_attention_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dvt_im2col": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dvt_vit_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float]),
+    "dvt_vit_destroy": (None, [c_void_p]),
+    "dvt_vit_load": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    "dvt_vit_reserve": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
+    "dvt_vit_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                c_void_p, c_int, c_void_p]),
 }
 
 

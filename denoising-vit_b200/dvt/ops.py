@@ -48,3 +48,38 @@ def gemm_tn_residual_(x: torch.Tensor, a: torch.Tensor, w: torch.Tensor, bias: t
     check(lib().dvt_gemm_tn_residual(ptr(a), a.stride(0), ptr(w), w.stride(0), _dt(a), M, N, K, ptr(bias), ptr(gamma),
                                      ptr(x), x.stride(0), cur_stream()), "dvt_gemm_tn_residual")
     return x
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6,
+              out_dtype: torch.dtype = torch.bfloat16, in_group: int = 1, skip: int = 0) -> torch.Tensor:
+    """Row LayerNorm of fp32 x [rows, C]; optional prefix strip (drop the first `skip` rows of every `in_group`)."""
+    _need_cuda(x, gamma, beta)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    rows, C = x.shape
+    out_rows = rows if skip == 0 else rows // in_group * (in_group - skip)
+    y = torch.empty((out_rows, C), device=x.device, dtype=out_dtype)
+    check(lib().dvt_layernorm(ptr(x), x.stride(0), ptr(gamma), ptr(beta), ptr(y), y.stride(0), _dt(y), rows, C, eps,
+                              in_group, skip, cur_stream()), "dvt_layernorm")
+    return y
+
+
+def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """qkv bf16 [B, N, 3*heads*64] (timm Attention.qkv output) -> bf16 [B, N, heads*64]."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape[2] == 3 * heads * 64
+    B, N, _ = qkv.shape
+    out = torch.empty((B, N, heads * 64), device=qkv.device, dtype=torch.bfloat16)
+    check(lib().dvt_attention_fwd(ptr(qkv), ptr(out), B, N, heads, cur_stream()), "dvt_attention_fwd")
+    return out
+
+
+def im2col(x: torch.Tensor, patch: int, stride: int) -> torch.Tensor:
+    """x [B,3,H,W] f32/bf16 -> bf16 [B*h*w, round_up(3*P*P, 8)]."""
+    _need_cuda(x)
+    assert x.dim() == 4 and x.shape[1] == 3 and x.is_contiguous()
+    B, _, H, W = x.shape
+    h, w = (H - patch) // stride + 1, (W - patch) // stride + 1
+    kp = (3 * patch * patch + 7) // 8 * 8
+    out = torch.empty((B * h * w, kp), device=x.device, dtype=torch.bfloat16)
+    check(lib().dvt_im2col(ptr(x), _dt(x), ptr(out), B, H, W, patch, stride, cur_stream()), "dvt_im2col")
+    return out

@@ -63,6 +63,47 @@ int dvt_gemm_tn(const void* A, int lda, const void* B, int ldb, int dtype, int M
 int dvt_gemm_tn_residual(const void* A, int lda, const void* B, int ldb, int dtype, int M, int N, int K,
                          const float* bias, const float* gamma, float* x_inout, int ldx, void* stream);
 
+/* y = LayerNorm(x) over rows of C fp32 (eps inside the sqrt, affine gamma/beta), output bf16 or fp32.
+ * in_group/skip: rows are grouped in runs of `in_group`; the first `skip` rows of every group are dropped and the
+ * output is compacted (used to strip prefix tokens); pass in_group=1, skip=0 for a plain LayerNorm.
+ * Replaces: nn.LayerNorm(eps=1e-6) in timm Block / VisionTransformer.norm. */
+int dvt_layernorm(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int y_dtype,
+                  int rows, int C, float eps, int in_group, int skip, void* stream);
+
+/* Multi-head attention, head_dim 64, no mask, scale 1/8: qkv bf16 [B, N, 3*heads*64] -> out bf16 [B, N, heads*64].
+ * Replaces: timm Attention.forward -> F.scaled_dot_product_attention
+ * (reference restatement: evaluation/vitdet/vision_transformer.py:73-91). */
+int dvt_attention_fwd(const void* qkv_bf16, void* out_bf16, int B, int N, int heads, void* stream);
+
+/* Patch extraction for Conv2d(3->C, kernel P, stride S): x [B,3,H,W] (f32 or bf16) -> bf16 [B*h*w, Kp],
+ * Kp = round_up(3*P*P, 8), column = c*P*P + i*P + j.  h = (H-P)/S+1, w = (W-P)/S+1
+ * (dvt/models/vit_wrapper.py:78-91: stride override + dynamic_feat_size). */
+int dvt_im2col(const void* x, int x_dtype, void* out_bf16, int B, int H, int W, int P, int S, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * HP-1: frozen ViT forward (replaces PretrainedViTWrapper.get_intermediate_layers,
+ * dvt/models/vit_wrapper.py:122-143, i.e. timm VisionTransformer.forward_intermediates)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct dvt_vit dvt_vit_t;
+
+/* prefix_tokens = 1 (cls) + number of register tokens.  Only head_dim 64 (embed == 64*heads). */
+int dvt_vit_create(dvt_vit_t** out, int embed, int depth, int heads, int patch, int mlp_hidden, int swiglu,
+                   int layerscale, int prefix_tokens, float ln_eps);
+void dvt_vit_destroy(dvt_vit_t* h);
+/* Loads one fp32 tensor by its timm state-dict key (without the wrapper's "model." prefix), e.g.
+ * "blocks.3.attn.qkv.weight".  `src` may be host or device memory.  cls_token / reg_token / pos_embed are not
+ * loaded here: the caller passes the (resampled) position table and the prefix rows to dvt_vit_forward. */
+int dvt_vit_load(dvt_vit_t* h, const char* timm_key, const float* src, size_t numel);
+/* Pre-sizes the activation workspaces (otherwise grown on first use). */
+int dvt_vit_reserve(dvt_vit_t* h, int max_batch, int H, int W, int stride);
+/* x: [B,3,H,W] f32 or bf16.  pos_patch: f32 [h*w, C] position embedding of the patch tokens for this grid
+ * (already resampled).  prefix_rows: f32 [prefix_tokens, C] rows written in front of the patches (cls + its
+ * position, register tokens).  Runs blocks 0..layer_index, applies the final LayerNorm if `norm`.
+ * out (f32): all_tokens == 0 -> [B, h, w, C] (prefix stripped, NHWC); all_tokens == 1 -> [B, prefix + h*w, C]. */
+int dvt_vit_forward(dvt_vit_t* h, const void* x, int x_dtype, int B, int H, int W, int stride,
+                    const float* pos_patch, const float* prefix_rows, int layer_index, int norm, float* out,
+                    int all_tokens, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

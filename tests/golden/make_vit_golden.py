@@ -3,7 +3,7 @@
 
 Run in the build container:  python tests/golden/make_vit_golden.py
 The .npz holds the input, the timm-named weights (fp16-free, float32) and HF's last_hidden_state.
-Sizes are kept tiny (embed 64, depth 2, 56x56 image, patch 14 -> 4x4 grid) so the fixture is a few hundred KB.
+Sizes are kept tiny (embed 64, 1 head of 64, depth 2, 56x56 image, patch 14 -> 4x4 grid) so the fixture is a few hundred KB.
 """
 import os
 import sys
@@ -24,7 +24,11 @@ def hf_to_timm(hf_sd, depth, with_reg):
         "norm.bias": hf_sd["layernorm.bias"],
     }
     if with_reg:
+        # timm's reg4 checkpoints are stored with no_embed_class=True: the cls position is folded into cls_token
+        # and pos_embed covers the patches only (timm vision_transformer.py checkpoint_filter_fn for DINOv2-reg).
         sd["reg_token"] = hf_sd["embeddings.register_tokens"]
+        sd["cls_token"] = sd["cls_token"] + sd["pos_embed"][:, :1]
+        sd["pos_embed"] = sd["pos_embed"][:, 1:]
     for i in range(depth):
         h = f"encoder.layer.{i}."
         t = f"blocks.{i}."
@@ -54,7 +58,7 @@ def hf_to_timm(hf_sd, depth, with_reg):
 def make(name, with_reg=False, swiglu=False, seed=0):
     import transformers
     torch.manual_seed(seed)
-    kw = dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=2, mlp_ratio=4, image_size=56, patch_size=14,
+    kw = dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=1, mlp_ratio=4, image_size=56, patch_size=14,
               layerscale_value=1.0, use_swiglu_ffn=swiglu, hidden_act="gelu", attention_probs_dropout_prob=0.0,
               hidden_dropout_prob=0.0, layer_norm_eps=1e-6)
     if with_reg:
@@ -81,7 +85,7 @@ def make(name, with_reg=False, swiglu=False, seed=0):
     sd = hf_to_timm(hf_sd, 2, with_reg)
     mlp_hidden = sd["blocks.0.mlp.fc1.weight"].shape[0]
     arrays = {"x": x.numpy(), "hf_last_hidden_state": out.numpy(),
-              "meta": np.array([64, 2, 2, 14, 56, mlp_hidden, int(swiglu), 4 if with_reg else 0], dtype=np.int64)}
+              "meta": np.array([64, 2, 1, 14, 56, mlp_hidden, int(swiglu), 4 if with_reg else 0], dtype=np.int64)}
     for k, v in sd.items():
         arrays["w:" + k] = v.numpy()
     path = os.path.join(HERE, f"vit_hf_{name}.npz")
