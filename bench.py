@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of DVT stage-1 denoising (ViT-B/14, 518x518, 768+1 views, 2000-iteration
+neural-field fit per image) on N B200s of one node.  One "step" = one image through both hot paths:
+HP-1 769 frozen-ViT forwards -> feature bank, HP-2 per-image fit + final 37x37 query.
+
+  python bench.py --gpus 1 --steps 3 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+  python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port), same metric
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM); `e2e` goes through the public
+per-image call with pinned HOST views, host->device copies and device->host result reads inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "denoising-vit_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+MODEL = "vit_base_patch14_dinov2.lvd142m"
+FLOPS_PER_VIEW = 303.1e9                 # 1.24 + 12 x (4.85 + 5.77 + 1.62 + 12.93) GF
+FIT_BYTES_P1, FIT_BYTES_P2 = 522e6, 505e6  # algorithmic bytes per fit step (dense Adam, 24 B/param)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--views", type=int, default=768)
+    ap.add_argument("--num-iters", type=int, default=2000)
+    ap.add_argument("--warmup-iters", type=int, default=200)
+    ap.add_argument("--extract-bsz", type=int, default=16)
+    ap.add_argument("--graph-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 6 and r[2 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port, fp32 PyTorch CPU) on a bounded sample, extrapolated per image
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(args, views_sample: int = 2, fit_steps: int = 4):
+    from oracle import fit as OF
+    from oracle import hashgrid as HG
+    from oracle import vit as OV
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = OV.CONFIGS[MODEL]
+    sd = OV.random_state_dict(cfg, seed=0)
+    x = torch.randn(1, 3, 518, 518, generator=torch.Generator().manual_seed(0))
+    OV.forward_intermediates(sd, cfg, x, [11])  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(views_sample):
+        OV.forward_intermediates(sd, cfg, x, [11])
+    t_view = (time.perf_counter() - t0) / views_sample
+    # fit steps at the full problem size (C 768, 37x37, 16 levels, 2048 pixels); small synthetic bank of 8 views
+    C, h, w, V, bsz = 768, 37, 37, 8, 2048
+    meta = HG.grid_meta(16)
+    feats, coords = OF.synthetic_bank(V, h, w, C, seed=0)
+    init = OF.init_params(C, h, w, meta, seed=0)
+    T = 2 * fit_steps + 2
+    idx = np.random.RandomState(0).randint(0, V * h * w, (T, bsz))
+    p = {k: init[k].clone().float().requires_grad_(True) for k in OF.PARAM_ORDER}
+    opt = torch.optim.Adam([p[k] for k in OF.PARAM_ORDER], lr=0.01, eps=1e-15, weight_decay=1e-5, betas=(0.9, 0.99))
+    g_all = OF.make_patch_coordinates(h, w).unsqueeze(0).repeat(V, 1, 1, 1).reshape(-1, 2)
+    f2, c2 = feats.reshape(-1, C), coords.reshape(-1, 2)
+    times = {False: [], True: []}
+    for step in range(T):
+        phase2 = step > T // 2
+        if phase2:
+            p["G"].requires_grad = False
+        t0 = time.perf_counter()
+        i = torch.from_numpy(idx[step])
+        out = OF.denoiser_forward(p, f2[i], c2[i], meta, g_all[i], phase2)
+        opt.zero_grad()
+        (out["loss"] * 1024.0).backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if step not in (0, T // 2 + 1):  # first step of each phase = warm-up
+            times[phase2].append(dt)
+    t_p1, t_p2 = float(np.mean(times[False])), float(np.mean(times[True]))
+    n_p2 = args.num_iters - 1 - int(0.5 * args.num_iters)
+    n_p1 = args.num_iters - n_p2
+    per_image = (args.views + 1) * t_view + n_p1 * t_p1 + n_p2 * t_p2
+    return {"value": 1.0 / per_image, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": (f"{views_sample} ViT-B/14 518^2 forwards ({t_view:.3f} s/view) + {len(times[False])}+{len(times[True])} "
+                       f"full-size fit steps ({t_p1:.3f} / {t_p2:.3f} s/step phase 1/2), extrapolated to "
+                       f"{args.views + 1} views + {args.num_iters} steps"),
+            "s_per_view": t_view, "s_per_step_phase1": t_p1, "s_per_step_phase2": t_p2}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    vals, last = [], None
+    for _ in range(max(1, args.warmup > 0) + args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference_rate(args, views_sample=1, fit_steps=2)
+        vals.append((last["value"], time.perf_counter() - t0))
+    vals = vals[1:] if len(vals) > 1 else vals
+    v = float(np.mean([a for a, _ in vals]))
+    last["value"] = v
+    line = {"metric": "images/sec stage-1 denoise (ViT-B/14, 518^2, 2k-iter fit)", "value": v, "unit": "images/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "stage1_vitb14_518_768views_2000iters", "note": "reference algorithm (oracle port, "
+                       "PyTorch CPU fp32) on a bounded sample per step, extrapolated to one image"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------
+def synthetic_coords(V, h, w, seed, device):
+    """Seeded crop-box stream (scale in [0.1, 0.5], ratio in [3/4, 4/3], p(flip) = 0.5) -> patch coordinates in [0,1];
+    last view = full image (main_img_denoising.py:288-294,337)."""
+    rs = np.random.RandomState(seed)
+    out = torch.zeros(V, h, w, 2)
+    for v in range(V - 1):
+        area = rs.uniform(0.1, 0.5)
+        ratio = np.exp(rs.uniform(np.log(3 / 4), np.log(4 / 3)))
+        cw, ch = min(1.0, np.sqrt(area * ratio)), min(1.0, np.sqrt(area / ratio))
+        x0, y0 = rs.uniform(0, 1 - cw), rs.uniform(0, 1 - ch)
+        xs, ys = torch.linspace(x0, x0 + cw, w), torch.linspace(y0, y0 + ch, h)
+        if rs.rand() < 0.5:
+            xs = xs.flip(0)
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        out[v] = torch.stack([gx, gy], -1)
+    ys, xs = torch.linspace(0, 1, h), torch.linspace(0, 1, w)
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    out[-1] = torch.stack([gx, gy], -1)
+    return out.clamp_(0, 1).to(device)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    import dvt.models as DVT
+    from dvt import _lib
+    from dvt.stage1 import Stage1Config, Stage1Pipeline
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    V = args.views + 1
+    vit = DVT.PretrainedViTWrapper(MODEL, stride=14)
+    with torch.no_grad():
+        for b in vit.model.blocks:  # non-degenerate LayerScale (DINOv2 init 1e-5 would switch the blocks off)
+            b.ls1.gamma.fill_(1.0)
+            b.ls2.gamma.fill_(1.0)
+    vit = vit.to(dev).eval()
+    cfg = Stage1Config(num_iters=args.num_iters, warmup_iters=args.warmup_iters, n_levels=16, extract_bsz=args.extract_bsz,
+                       pixel_bsz=2048, graph_steps=args.graph_steps)
+    pipe = Stage1Pipeline(vit, layer_index=11, input_size=(518, 518), cfg=cfg)
+    h, w, C = pipe.h, pipe.w, pipe.C
+
+    # synthetic inputs: views larger than L2 (2.48 GB fp32), host copy pinned for the e2e leg
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    views_dev = torch.randn(V, 3, 518, 518, device=dev, generator=g)
+    coords = synthetic_coords(V, h, w, seed=rank, device=dev)
+    n_rows = V * h * w
+
+    def idx_stream(step):
+        return np.random.RandomState(1000 * rank + step).randint(0, n_rows, (args.num_iters, 2048))
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    seg = {"hp1": [], "hp2": []}
+
+    def one_image(step, views, record=False, to_host=False):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        bank = pipe.extract_bank(views)
+        e1.record()
+        idx = idx_stream(step)                      # host work overlapped with the queued ViT forwards
+        out = pipe.denoise(bank, coords, idx, seed=None)
+        e2.record()
+        if record:
+            seg["hp1"].append((e0, e1))
+            seg["hp2"].append((e1, e2))
+        if to_host:
+            return out["denoised_feats"].cpu(), out["raw"].cpu()
+        return out["denoised_feats"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step, steps, collate):
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = _lib.lib().dvt_launch_count()
+        t0, t1 = ev(), ev()
+        t0.record()
+        outs = [run_step(args.warmup + i) for i in range(steps)]
+        if collate and world > 1:  # the single exchange of the path: collate denoised maps for stage 2
+            mine = torch.cat([o if torch.is_tensor(o) else o[0].to(dev) for o in outs], 0).contiguous()
+            gathered = torch.empty((world,) + tuple(mine.shape), device=dev, dtype=mine.dtype)
+            dist.all_gather_into_tensor(gathered, mine)
+        t1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks, _lib.lib().dvt_launch_count() - l0
+
+    for i in range(args.warmup):
+        one_image(i, views_dev)
+    ms_total, clocks, launches = timed(lambda s: one_image(s, views_dev, record=True), args.steps, collate=True)
+    torch.cuda.synchronize()
+    value = world * args.steps / (ms_total / 1000.0)
+    hp1_ms = float(np.mean([a.elapsed_time(b) for a, b in seg["hp1"]]))
+    hp2_ms = float(np.mean([a.elapsed_time(b) for a, b in seg["hp2"]]))
+
+    e2e = None
+    if not args.no_e2e:
+        views_host = torch.empty((V, 3, 518, 518), dtype=torch.float32).pin_memory()
+        views_host.copy_(views_dev)
+        del views_dev
+        torch.cuda.empty_cache()
+        one_image(0, views_host, to_host=True)  # warm the staging buffers
+        ms_e2e, _, _ = timed(lambda s: one_image(s, views_host, to_host=True), args.steps, collate=True)
+        h2d = V * 3 * 518 * 518 * 4 + args.num_iters * 2048 * 4
+        d2h = 2 * h * w * C * 4
+        e2e = {"value": world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps}
+
+    if rank == 0:
+        pk = peaks()
+        n_p2 = args.num_iters - 1 - int(0.5 * args.num_iters)
+        n_p1 = args.num_iters - n_p2
+        hp1_tf = V * FLOPS_PER_VIEW / (hp1_ms / 1e3) / 1e12
+        hp2_gbs = (n_p1 * FIT_BYTES_P1 + n_p2 * FIT_BYTES_P2) / (hp2_ms / 1e3) / 1e9
+        r1 = {"bound": "tensor", "achieved": hp1_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+              "frac": hp1_tf / pk["bf16_tflops"], "traffic": None, "kernel": "HP-1: 769 ViT-B/14 forwards (tcgen05 GEMMs + "
+              "flash attention)", "ms_per_image": hp1_ms, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)"}
+        r2 = {"bound": "hbm", "achieved": hp2_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hp2_gbs / pk["hbm_gbs"],
+              "traffic": None, "kernel": "HP-2: 2000-step neural-field fit (dense Adam sweep dominates)",
+              "ms_per_image": hp2_ms, "peak_source": pk["source"] + " (copy bandwidth)"}
+        dominant, other = (r1, r2) if hp1_ms >= hp2_ms else (r2, r1)
+        line = {"metric": "images/sec stage-1 denoise (ViT-B/14, 518^2, 2k-iter fit)", "value": value, "unit": "images/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (ViT) / tf32x3 (fit)",
+                "data": "synthetic",
+                "config": {"workload": "stage1_vitb14_518_768views_2000iters", "views_per_image": V,
+                           "fit_iters": args.num_iters, "fit_warmup_iters": args.warmup_iters, "pixel_bsz": 2048,
+                           "n_levels": 16, "extract_bsz": args.extract_bsz, "images_per_gpu": args.steps,
+                           "parallelism": f"image-sharded x{world}, one all-gather of denoised maps",
+                           "l2": "inputs larger than L2 (2.48 GB of views, 3.2 GB bank, 0.34 GB Adam state per image)"},
+                "clocks": clocks, "gpu_launches": int(launches), "roofline": dominant, "roofline_other": other}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_rate(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

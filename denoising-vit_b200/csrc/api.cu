@@ -16,6 +16,24 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
                 cudaStream_t stream, int impl);
 int vit_patch(const Vit* v);
 int vit_prefix(const Vit* v);
+struct Fit;
+int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const float* scale, const uint32_t* res,
+               const uint32_t* size, const uint32_t* offset, const uint32_t* hashed);
+void fit_destroy(Fit* f);
+int fit_set_param(Fit* f, const char* name, const float* src, size_t numel);
+int fit_get_param(Fit* f, const char* name, float* dst, size_t numel);
+int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, const int* idx_host, int num_iters,
+              float lr, float min_lr, int warmup_iters, float freeze_after, float weight_decay, float loss_scale);
+int fit_run(Fit* f, int count, int use_graphs, cudaStream_t st, int impl);
+int fit_losses(Fit* f, float* dst_host, int num_iters);
+int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, int impl);
+int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, int impl);
+int hashgrid_corners(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
+                     const uint32_t* hashed, const float* coords, int n, uint32_t* idx, float* w, cudaStream_t st);
+int hashgrid_fwd(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
+                 const uint32_t* hashed, const float* table, const float* coords, int n, float* out, cudaStream_t st);
+int hashgrid_bwd(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
+                 const uint32_t* hashed, const float* coords, int n, const float* dout, float* gtable, cudaStream_t st);
 const char* last_error();
 extern int g_debug_impl_override;
 int g_debug_impl_override = -1;
@@ -39,6 +57,8 @@ int dvt_device_error(unsigned int* code_out) {
   if (code_out) *code_out = v;
   return DVT_OK;
 }
+
+long long dvt_launch_count(void) { return dvt::launch_count(); }
 
 int dvt_set_debug_impl(int impl) {
   if (impl != 0 && impl != 1 && impl != -1) {
@@ -133,6 +153,107 @@ int dvt_vit_forward(dvt_vit_t* h, const void* x, int x_dtype, int B, int H, int 
   DVT_REQUIRE(h, "dvt_vit_forward: null handle");
   return vit_forward(reinterpret_cast<Vit*>(h), x, x_dtype == DVT_DTYPE_BF16, B, H, W, stride, pos_patch, prefix_rows,
                      layer_index, norm, out, all_tokens, reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+
+int dvt_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
+                     void* out, int ldo, int out_dtype, int splits, float* last_col_out, void* stream) {
+  DVT_REQUIRE(A && B && out, "dvt_gemm_bf16_ex: null pointer");
+  GemmEpi e;
+  e.out = out;
+  e.ldo = ldo;
+  if (splits > 1 || last_col_out) {
+    DVT_REQUIRE(out_dtype == DVT_DTYPE_F32, "dvt_gemm_bf16_ex: split-K / last_col_out need fp32 output");
+    e.out_mode = OUT_F32_ATOMIC;
+    e.last_col_out = last_col_out;
+  } else {
+    e.out_mode = out_dtype == DVT_DTYPE_BF16 ? OUT_BF16 : OUT_F32;
+  }
+  GemmShape s{M, N, K, splits < 1 ? 1 : splits};
+  s.a_mn = a_mn;
+  s.b_mn = b_mn;
+  return launch_gemm_tn(A, lda, B, ldb, TMAP_BF16, s, e, reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+
+int dvt_gemm_f32x3(const float* A, int lda, size_t plane_a, int a_mn, const float* B, int ldb, size_t plane_b, int b_mn,
+                   int M, int N, int K, float* out, int ldo, int splits, float* last_col_out, void* stream) {
+  DVT_REQUIRE(A && B && out, "dvt_gemm_f32x3: null pointer");
+  GemmEpi e;
+  e.out = out;
+  e.ldo = ldo;
+  if (splits > 1 || last_col_out) {
+    e.out_mode = OUT_F32_ATOMIC;
+    e.last_col_out = last_col_out;
+  } else {
+    e.out_mode = OUT_F32;
+  }
+  GemmShape s{M, N, K, splits < 1 ? 1 : splits};
+  s.a_mn = a_mn; s.b_mn = b_mn; s.x3 = 1; s.plane_a = plane_a; s.plane_b = plane_b;
+  return launch_gemm_tn(A, lda, B, ldb, TMAP_F32, s, e, reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+
+int dvt_hashgrid_corners(int n_levels, const float* scale_host, const uint32_t* res_host, const uint32_t* size_host,
+                         const uint32_t* offset_host, const uint32_t* hashed_host, const float* coords, int n,
+                         uint32_t* idx_out, float* w_out, void* stream) {
+  DVT_REQUIRE(scale_host && res_host && size_host && offset_host && hashed_host && coords && idx_out && w_out && n > 0,
+              "dvt_hashgrid_corners: bad arguments");
+  return hashgrid_corners(n_levels, scale_host, res_host, size_host, offset_host, hashed_host, coords, n, idx_out, w_out,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_hashgrid_fwd(int n_levels, const float* scale_host, const uint32_t* res_host, const uint32_t* size_host,
+                     const uint32_t* offset_host, const uint32_t* hashed_host, const float* table, const float* coords,
+                     int n, float* out, void* stream) {
+  DVT_REQUIRE(scale_host && res_host && size_host && offset_host && hashed_host && table && coords && out && n > 0,
+              "dvt_hashgrid_fwd: bad arguments");
+  return hashgrid_fwd(n_levels, scale_host, res_host, size_host, offset_host, hashed_host, table, coords, n, out,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_hashgrid_bwd(int n_levels, const float* scale_host, const uint32_t* res_host, const uint32_t* size_host,
+                     const uint32_t* offset_host, const uint32_t* hashed_host, const float* coords, int n,
+                     const float* dout, float* grad_table, void* stream) {
+  DVT_REQUIRE(scale_host && res_host && size_host && offset_host && hashed_host && coords && dout && grad_table && n > 0,
+              "dvt_hashgrid_bwd: bad arguments");
+  return hashgrid_bwd(n_levels, scale_host, res_host, size_host, offset_host, hashed_host, coords, n, dout, grad_table,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dvt_fit_create(dvt_fit_t** out, int feat_dim, int gh, int gw, int bsz, int n_levels, const float* scale_host,
+                   const uint32_t* res_host, const uint32_t* size_host, const uint32_t* offset_host,
+                   const uint32_t* hashed_host) {
+  DVT_REQUIRE(out && scale_host && res_host && size_host && offset_host && hashed_host, "dvt_fit_create: null argument");
+  return fit_create(reinterpret_cast<Fit**>(out), feat_dim, gh, gw, bsz, n_levels, scale_host, res_host, size_host,
+                    offset_host, hashed_host);
+}
+void dvt_fit_destroy(dvt_fit_t* h) { fit_destroy(reinterpret_cast<Fit*>(h)); }
+int dvt_fit_set_param(dvt_fit_t* h, const char* name, const float* src, size_t numel) {
+  DVT_REQUIRE(h && name && src, "dvt_fit_set_param: null argument");
+  return fit_set_param(reinterpret_cast<Fit*>(h), name, src, numel);
+}
+int dvt_fit_get_param(dvt_fit_t* h, const char* name, float* dst, size_t numel) {
+  DVT_REQUIRE(h && name && dst, "dvt_fit_get_param: null argument");
+  return fit_get_param(reinterpret_cast<Fit*>(h), name, dst, numel);
+}
+int dvt_fit_begin(dvt_fit_t* h, const float* bank_feats, const float* bank_coords, size_t bank_rows,
+                  const int32_t* idx_host, int num_iters, float lr, float min_lr, int warmup_iters, float freeze_after,
+                  float weight_decay, float loss_scale) {
+  DVT_REQUIRE(h, "dvt_fit_begin: null handle");
+  return fit_begin(reinterpret_cast<Fit*>(h), bank_feats, bank_coords, bank_rows, idx_host, num_iters, lr, min_lr,
+                   warmup_iters, freeze_after, weight_decay, loss_scale);
+}
+int dvt_fit_run(dvt_fit_t* h, int count, int graph_steps, void* stream) {
+  DVT_REQUIRE(h, "dvt_fit_run: null handle");
+  return fit_run(reinterpret_cast<Fit*>(h), count, graph_steps, reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+int dvt_fit_losses(dvt_fit_t* h, float* dst_host, int num_iters) {
+  DVT_REQUIRE(h && dst_host, "dvt_fit_losses: null argument");
+  return fit_losses(reinterpret_cast<Fit*>(h), dst_host, num_iters);
+}
+int dvt_fit_query(dvt_fit_t* h, const float* coords, int n, float* out, void* stream) {
+  DVT_REQUIRE(h, "dvt_fit_query: null handle");
+  return fit_query(reinterpret_cast<Fit*>(h), coords, n, out, reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+int dvt_fit_residual(dvt_fit_t* h, const float* raw, int n, float* out, void* stream) {
+  DVT_REQUIRE(h, "dvt_fit_residual: null handle");
+  return fit_residual(reinterpret_cast<Fit*>(h), raw, n, out, reinterpret_cast<cudaStream_t>(stream), eff_impl());
 }
 
 }  // extern "C"

@@ -336,9 +336,10 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     dim3 grid(N, heads, B);
     attention_simt_kernel<<<grid, 32, N * sizeof(float), stream>>>(qkv, out, N, C, scale);
     DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
     return DVT_OK;
   }
-  static bool attr_set = false;
+  static bool attr_set = false;  // (attention is never launched inside a stream capture)
   if (!attr_set) {
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
     attr_set = true;
@@ -350,6 +351,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
   attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(tm, out, N, C, scale * 1.4426950408889634f);
   DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
   return DVT_OK;
 }
 

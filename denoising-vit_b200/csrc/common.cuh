@@ -313,8 +313,13 @@ int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t rows
                  uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols);
 // 3-D tensor [d2, d1, d0(contiguous)] with byte strides for d1 and d2; box = [1, box1, box0].
 int make_tmap_3d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2 = 1,
+                 bool swizzle_atom32 = false /* CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: MN-major TF32 operands */);
 
 int num_sms();
+
+// host-side tally of kernels launched by this library (graph replays add the node count of the graph)
+void count_launch(long long n = 1);
+long long launch_count();
 
 }  // namespace dvt

@@ -4,4 +4,5 @@
 #include "vit_kernels.cu"
 #include "attention.cu"
 #include "vit.cu"
+#include "fit.cu"
 #include "api.cu"

@@ -1,0 +1,939 @@
+// HP-2: per-image neural-field denoiser fit (stage 1), no tiny-cuda-nn.
+// Replaces the hot loop of `denoise_an_image` (main_img_denoising.py:67-89): SingleImageDenoiser.forward
+// (dvt/models/offline_denoiser.py:92-140) + NeuralFeatureField (dvt/models/neural_feature_field.py:25-49, tcnn
+// HashGrid + 2-layer MLP) + torch.optim.Adam with the reference's exact quirks (dense hash-grid gradient ->
+// dense Adam sweep, loss scale never unscaled, per-parameter step counters, G frozen / residual MLP started after
+// `freeze_step`).
+//
+// One step = a fixed sequence of kernels on one stream (captured into CUDA graphs of several steps by the host):
+//   encode (index -> coords -> hash-grid gather/interp -> bf16)            [+ phase 2: gather raw rows -> bf16]
+//   GEMM  h1 = relu(enc W1^T + b1)        GEMM  F = h1 W2^T + b2            [+ residual MLP forward, 3 GEMMs]
+//   loss  (pred = F + G[r,c] (+R), MSE + cosine, d pred, dG atomics, loss log) [+ residual losses, dR]
+//   GEMM  dh1 = (dpred W2) * relu'        GEMM  dW2|db2 += dpred^T [h1|1]   GEMM dW1|db1 += dh1^T [enc|1]
+//   GEMM  denc = dh1 W1                   grid backward (vector atomics into the dense table gradient)
+//   [+ residual MLP backward, 5 GEMMs]    Adam(table) dense sweep           Adam(small params) + bf16 mirrors
+// All GEMMs run on tcgen05 (gemm.cu) as 3xTF32 products of fp32 hi/lo planes (fp32-accurate: bf16 operands cannot
+// hold the cosine >= 0.999 parity bar); weight-gradient GEMMs read the activations as MN-major
+// operands, so no transposed copies exist; bias gradients come from a ones column appended to the activation buffers.
+//
+// HBM layout: table p/m/v/g as four fp32 arrays of n_entries*8; "small" params (field MLP, G as [h*w, C],
+// residual MLP) in one flat fp32 buffer with identically laid out m / v / grad buffers and TF32 hi/lo operand planes.
+#include "common.cuh"
+#include "gemm.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace dvt {
+
+constexpr int FIT_MAX_LEVELS = 16;
+constexpr int FIT_F = 8;  // features per level
+
+struct GridLevels {
+  int n_levels;
+  float scale[FIT_MAX_LEVELS];
+  uint32_t res[FIT_MAX_LEVELS];
+  uint32_t size[FIT_MAX_LEVELS];
+  uint32_t offset[FIT_MAX_LEVELS + 1];
+  uint32_t hashed[FIT_MAX_LEVELS];
+};
+
+// tcnn grid_index for 2-D inputs (oracle/hashgrid.py::corner_indices_weights restates the published algorithm)
+__device__ __forceinline__ uint32_t grid_index(const GridLevels& g, int l, uint32_t x, uint32_t y) {
+  uint32_t idx = g.hashed[l] ? (x ^ (y * 2654435761u)) : (x + y * g.res[l]);
+  return idx % g.size[l];
+}
+
+struct CornerSet {
+  uint32_t idx[4];
+  float w[4];
+};
+
+__device__ __forceinline__ CornerSet grid_corners(const GridLevels& g, int l, float x, float y) {
+  const float s = g.scale[l];
+  float px = fmaf(s, x, 0.5f), py = fmaf(s, y, 0.5f);
+  const float fx = floorf(px), fy = floorf(py);
+  const uint32_t cx = (uint32_t)(int)fx, cy = (uint32_t)(int)fy;
+  px -= fx;
+  py -= fy;
+  CornerSet c;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dx = k & 1, dy = k >> 1;
+    c.idx[k] = g.offset[l] + grid_index(g, l, cx + dx, cy + dy);
+    c.w[k] = (dx ? px : 1.f - px) * (dy ? py : 1.f - py);
+  }
+  return c;
+}
+
+// The bank rows sampled at step s are idx_all[s * n .. s * n + n).  Inside a captured CUDA graph the step is not
+// a launch-time constant, so kernels take (idx_all, step_base, step_off) and resolve s = *step_base + step_off on
+// the device; idx_all == nullptr means "row i" (query mode).
+struct StepRows {
+  const int* idx_all;
+  const int* step_base;
+  int step_off;
+  __device__ __forceinline__ int step() const { return *step_base + step_off; }
+  __device__ __forceinline__ const int* rows(int n) const {
+    return idx_all ? idx_all + (size_t)step() * n : nullptr;
+  }
+};
+
+// ----------------------------------------------------------------------------------------------------
+// encode: one thread per (sample, level).
+// ----------------------------------------------------------------------------------------------------
+__global__ void fit_encode_kernel(GridLevels g, const float* __restrict__ table, const float* __restrict__ coords,
+                                  StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * g.n_levels) return;
+  const int i = t % n, l = t / n;
+  const int* rows = sr.rows(n);
+  const int r = rows ? rows[i] : i;
+  const float2 xy = *reinterpret_cast<const float2*>(coords + 2 * (size_t)r);
+  const CornerSet c = grid_corners(g, l, xy.x, xy.y);
+  float acc[FIT_F];
+#pragma unroll
+  for (int f = 0; f < FIT_F; ++f) acc[f] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4* p = reinterpret_cast<const float4*>(table + (size_t)c.idx[k] * FIT_F);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    acc[0] = fmaf(c.w[k], a.x, acc[0]); acc[1] = fmaf(c.w[k], a.y, acc[1]);
+    acc[2] = fmaf(c.w[k], a.z, acc[2]); acc[3] = fmaf(c.w[k], a.w, acc[3]);
+    acc[4] = fmaf(c.w[k], b.x, acc[4]); acc[5] = fmaf(c.w[k], b.y, acc[5]);
+    acc[6] = fmaf(c.w[k], b.z, acc[6]); acc[7] = fmaf(c.w[k], b.w, acc[7]);
+  }
+  float hi[FIT_F], lo[FIT_F];
+#pragma unroll
+  for (int f = 0; f < FIT_F; ++f) {
+    hi[f] = tf32_hi(acc[f]);
+    lo[f] = acc[f] - hi[f];
+  }
+  float* dst = enc + (size_t)i * ld_enc + l * FIT_F;
+  *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+  *reinterpret_cast<float4*>(dst + plane) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<float4*>(dst + plane + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+}
+
+// fp32 encode (unit-test entry point: bit-level check of indices / weights against the oracle)
+__global__ void fit_encode_f32_kernel(GridLevels g, const float* __restrict__ table, const float* __restrict__ coords,
+                                      int n, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * g.n_levels) return;
+  const int i = t % n, l = t / n;
+  const float2 xy = *reinterpret_cast<const float2*>(coords + 2 * (size_t)i);
+  const CornerSet c = grid_corners(g, l, xy.x, xy.y);
+  for (int f = 0; f < FIT_F; ++f) {
+    float a = 0.f;
+    for (int k = 0; k < 4; ++k) a = fmaf(c.w[k], table[(size_t)c.idx[k] * FIT_F + f], a);
+    out[(size_t)i * g.n_levels * FIT_F + l * FIT_F + f] = a;
+  }
+}
+
+// corner indices + weights (unit-test entry point; "bit-exact patch indexing")
+__global__ void fit_corners_kernel(GridLevels g, const float* __restrict__ coords, int n, uint32_t* __restrict__ idx,
+                                   float* __restrict__ w) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * g.n_levels) return;
+  const int i = t % n, l = t / n;
+  const CornerSet c = grid_corners(g, l, coords[2 * i], coords[2 * i + 1]);
+  for (int k = 0; k < 4; ++k) {
+    idx[((size_t)i * g.n_levels + l) * 4 + k] = c.idx[k];
+    w[((size_t)i * g.n_levels + l) * 4 + k] = c.w[k];
+  }
+}
+
+// backward of the encoding: dense-table gradient accumulation with vector atomics
+__global__ void fit_grid_bwd_kernel(GridLevels g, const float* __restrict__ coords, StepRows sr, int n,
+                                    const float* __restrict__ denc, int ld_denc, float* __restrict__ gtable) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * g.n_levels) return;
+  const int i = t % n, l = t / n;
+  const int* rows = sr.rows(n);
+  const int r = rows ? rows[i] : i;
+  const float2 xy = *reinterpret_cast<const float2*>(coords + 2 * (size_t)r);
+  const CornerSet c = grid_corners(g, l, xy.x, xy.y);
+  const float4 a = *reinterpret_cast<const float4*>(denc + (size_t)i * ld_denc + l * FIT_F);
+  const float4 b = *reinterpret_cast<const float4*>(denc + (size_t)i * ld_denc + l * FIT_F + 4);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float* dst = gtable + (size_t)c.idx[k] * FIT_F;
+    const float w = c.w[k];
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w * a.x), "f"(w * a.y), "f"(w * a.z),
+                 "f"(w * a.w)
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(w * b.x), "f"(w * b.y),
+                 "f"(w * b.z), "f"(w * b.w)
+                 : "memory");
+  }
+}
+
+// gather bank rows (fp32) -> hi/lo planes [n, ld] (input of the residual MLP)
+__global__ void fit_gather_rows_kernel(const float* __restrict__ bank, int C, StepRows sr, int n,
+                                       float* __restrict__ out, int ld, size_t plane) {
+  const int i = blockIdx.x;
+  const int* rows = sr.rows(n);
+  const float4* src = reinterpret_cast<const float4*>(bank + (size_t)(rows ? rows[i] : i) * C);
+  for (int c4 = threadIdx.x; c4 < C / 4; c4 += blockDim.x) {
+    const float4 v = __ldg(src + c4);
+    const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    float* dst = out + (size_t)i * ld + c4 * 4;
+    *reinterpret_cast<float4*>(dst) = hi;
+    *reinterpret_cast<float4*>(dst + plane) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// loss + gradient kernel: one warp per sampled row (C % 4 == 0, C <= 1536).
+// losses[5] (this step's slots) accumulates: total, patch_l2, cosine, residual, residual_sparsity.
+// ----------------------------------------------------------------------------------------------------
+struct LossArgs {
+  const float* bank;        // [Nb, C] raw ViT features
+  StepRows sr;              // bank rows of this step
+  const float* F;           // [n, C] field output
+  const float* G;           // [hw, C] shared artifact map (fp32 master)
+  const float* R;           // [n, C] residual prediction or nullptr (phase 1)
+  float* dpred;             // [2 planes][n, C] (hi / lo)
+  float* dR;                // [2 planes][n, C] or nullptr
+  size_t plane;             // n * C
+  float* gG;                // [hw, C] gradient accumulator or nullptr (G frozen)
+  float* losses;            // [num_iters, 5]; this step's slots are used
+  int n, C, hw;
+  float loss_scale;
+};
+
+__global__ void fit_loss_kernel(LossArgs a) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= a.n) return;
+  const int C = a.C, nvec = C >> 2;
+  const int br = a.sr.rows(a.n)[row];
+  float* losses = a.losses + (size_t)a.sr.step() * 5;
+  const int cell = br % a.hw;  // exact (r, c) of the patch inside its view: the "shared artifact coordinate"
+  const float4* raw4 = reinterpret_cast<const float4*>(a.bank + (size_t)br * C);
+  const float4* F4 = reinterpret_cast<const float4*>(a.F + (size_t)row * C);
+  const float4* G4 = reinterpret_cast<const float4*>(a.G + (size_t)cell * C);
+  const float4* R4 = a.R ? reinterpret_cast<const float4*>(a.R + (size_t)row * C) : nullptr;
+  float4 pred[12], raw[12];
+  float dot = 0.f, pp = 0.f, rr = 0.f, sse = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      const float4 f = F4[v], gg = __ldg(G4 + v), r = __ldg(raw4 + v);
+      float4 p = make_float4(f.x + gg.x, f.y + gg.y, f.z + gg.z, f.w + gg.w);
+      if (R4) {
+        const float4 rp = R4[v];
+        p.x += rp.x; p.y += rp.y; p.z += rp.z; p.w += rp.w;
+      }
+      pred[i] = p;
+      raw[i] = r;
+      dot += p.x * r.x + p.y * r.y + p.z * r.z + p.w * r.w;
+      pp += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+      rr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+      const float dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z, dw = p.w - r.w;
+      sse += dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+  }
+  dot = warp_sum(dot); pp = warp_sum(pp); rr = warp_sum(rr); sse = warp_sum(sse);
+  const float np_ = fmaxf(sqrtf(pp), 1e-8f), nr_ = fmaxf(sqrtf(rr), 1e-8f);  // F.cosine_similarity eps
+  const float cosv = dot / (np_ * nr_);
+  const float inv_nc = 1.f / ((float)a.n * (float)C), inv_n = 1.f / (float)a.n;
+  // d/dpred [ mean((p-r)^2) + 1 - mean_rows cos ] * loss_scale
+  const float k_mse = 2.f * inv_nc * a.loss_scale;
+  const float k_cr = -inv_n * a.loss_scale / (np_ * nr_);   // coefficient of raw
+  const float k_cp = inv_n * a.loss_scale * cosv / (np_ * np_);  // coefficient of pred
+  float res_sq = 0.f, res_abs = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      const float4 p = pred[i], r = raw[i];
+      float4 d;
+      d.x = k_mse * (p.x - r.x) + k_cr * r.x + k_cp * p.x;
+      d.y = k_mse * (p.y - r.y) + k_cr * r.y + k_cp * p.y;
+      d.z = k_mse * (p.z - r.z) + k_cr * r.z + k_cp * p.z;
+      d.w = k_mse * (p.w - r.w) + k_cr * r.w + k_cp * p.w;
+      {
+        const float4 hi = make_float4(tf32_hi(d.x), tf32_hi(d.y), tf32_hi(d.z), tf32_hi(d.w));
+        float* dp = a.dpred + (size_t)row * C + v * 4;
+        *reinterpret_cast<float4*>(dp) = hi;
+        *reinterpret_cast<float4*>(dp + a.plane) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
+      }
+      if (a.gG) {
+        float* dst = a.gG + (size_t)cell * C + v * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+                     : "memory");
+      }
+      if (R4) {
+        // gt_residual = raw - denoised - shared = raw - (pred - R); e = R - gt = pred - raw
+        const float4 rp = R4[v];
+        const float ex = p.x - r.x, ey = p.y - r.y, ez = p.z - r.z, ew = p.w - r.w;
+        res_sq += ex * ex + ey * ey + ez * ez + ew * ew;
+        res_abs += fabsf(rp.x) + fabsf(rp.y) + fabsf(rp.z) + fabsf(rp.w);
+        const float k1 = 0.2f * inv_nc * a.loss_scale, k2 = 0.02f * inv_nc * a.loss_scale;
+        auto sgn = [](float x) { return (float)((x > 0.f) - (x < 0.f)); };
+        const float4 dr = make_float4(k1 * ex + k2 * sgn(rp.x), k1 * ey + k2 * sgn(rp.y), k1 * ez + k2 * sgn(rp.z),
+                                      k1 * ew + k2 * sgn(rp.w));
+        const float4 hi = make_float4(tf32_hi(dr.x), tf32_hi(dr.y), tf32_hi(dr.z), tf32_hi(dr.w));
+        float* dp = a.dR + (size_t)row * C + v * 4;
+        *reinterpret_cast<float4*>(dp) = hi;
+        *reinterpret_cast<float4*>(dp + a.plane) = make_float4(dr.x - hi.x, dr.y - hi.y, dr.z - hi.z, dr.w - hi.w);
+      }
+    }
+  }
+  if (R4) {
+    res_sq = warp_sum(res_sq);
+    res_abs = warp_sum(res_abs);
+  }
+  if (lane == 0) {
+    const float l2 = sse * inv_nc, lc = (1.f - cosv) * inv_n;
+    const float lr = 0.1f * res_sq * inv_nc, ls = 0.02f * res_abs * inv_nc;
+    atomicAdd(losses + 0, l2 + lc + lr + ls);
+    atomicAdd(losses + 1, l2);
+    atomicAdd(losses + 2, lc);
+    if (R4) {
+      atomicAdd(losses + 3, lr);
+      atomicAdd(losses + 4, ls);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics: L2 weight decay folded into the gradient, bias-corrected, eps outside sqrt)
+//   g' = g + wd p;  m += (g' - m)(1-b1);  v = b2 v + (1-b2) g'^2;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps)
+// step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are precomputed per step in double on the host.
+// ----------------------------------------------------------------------------------------------------
+struct AdamScalars {
+  float step_size, bc2_sqrt;
+};
+
+__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float wd, float ss, float bc2s) {
+  g = fmaf(wd, p, g);
+  m = fmaf(g - m, 0.1f, m);                 // lerp(m, g, 1 - beta1), beta1 = 0.9
+  v = fmaf(v, 0.99f, 0.01f * g * g);        // beta2 = 0.99
+  const float denom = sqrtf(v) / bc2s + 1e-15f;
+  p = p - ss * (m / denom);
+}
+
+__global__ void fit_adam_table_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
+                                      float4* __restrict__ g, size_t nvec, const AdamScalars* __restrict__ sc,
+                                      const int* __restrict__ step_base, int step_off, float wd) {
+  const AdamScalars s = sc[*step_base + step_off];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    const float4 gg = g[i];
+    adam1(pp.x, mm.x, vv.x, gg.x, wd, s.step_size, s.bc2_sqrt);
+    adam1(pp.y, mm.y, vv.y, gg.y, wd, s.step_size, s.bc2_sqrt);
+    adam1(pp.z, mm.z, vv.z, gg.z, wd, s.step_size, s.bc2_sqrt);
+    adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.bc2_sqrt);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// small params: one flat buffer; [g_lo, g_hi) is G, [r_lo, r_hi) the residual MLP, the rest the field MLP.
+__global__ void fit_adam_small_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
+                                      float4* __restrict__ g, float* __restrict__ wsplit, int nvec, int g_lo,
+                                      int g_hi, int r_lo, int r_hi, const AdamScalars* __restrict__ sc_main,
+                                      const AdamScalars* __restrict__ sc_res, const int* __restrict__ step_base,
+                                      int step_off, int freeze_step, float wd) {
+  const int step = *step_base + step_off;
+  const bool phase2 = step > freeze_step;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+    const bool is_g = i >= g_lo && i < g_hi, is_r = i >= r_lo && i < r_hi;
+    if ((is_g && phase2) || (is_r && !phase2)) continue;  // grad is None in the reference: Adam skips the tensor
+    const AdamScalars s = is_r ? sc_res[step] : sc_main[step];
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    const float4 gg = g[i];
+    adam1(pp.x, mm.x, vv.x, gg.x, wd, s.step_size, s.bc2_sqrt);
+    adam1(pp.y, mm.y, vv.y, gg.y, wd, s.step_size, s.bc2_sqrt);
+    adam1(pp.z, mm.z, vv.z, gg.z, wd, s.step_size, s.bc2_sqrt);
+    adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.bc2_sqrt);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!is_g) {  // GEMM operand planes of the weights
+      const float4 hi = make_float4(tf32_hi(pp.x), tf32_hi(pp.y), tf32_hi(pp.z), tf32_hi(pp.w));
+      *reinterpret_cast<float4*>(wsplit + (size_t)i * 4) = hi;
+      *reinterpret_cast<float4*>(wsplit + (size_t)(nvec + i) * 4) =
+          make_float4(pp.x - hi.x, pp.y - hi.y, pp.z - hi.z, pp.w - hi.w);
+    }
+  }
+}
+
+__global__ void fit_advance_kernel(int* step_base, int by) { *step_base += by; }
+
+__global__ void fit_fill_col_kernel(float* buf, int ld, int col, int rows, float val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) buf[(size_t)i * ld + col] = val;
+}
+
+__global__ void fit_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  // out[c, r] = in[r, c]
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / cols, c = e - r * cols;
+    out[c * rows + r] = in[e];
+  }
+}
+
+__global__ void fit_split_kernel(const float* __restrict__ p, float* __restrict__ wsplit, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float v = p[e], hi = tf32_hi(v);
+    wsplit[e] = hi;
+    wsplit[n + e] = v - hi;
+  }
+}
+
+__global__ void fit_coord_range_kernel(const float* __restrict__ coords, size_t n2, int* __restrict__ bad) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
+    const float c = coords[e];
+    if (!(c >= 0.f && c <= 1.f)) atomicExch(bad, 1);
+  }
+}
+
+// ====================================================================================================
+// host engine
+// ====================================================================================================
+struct Seg {
+  int off = 0, rows = 0, cols = 0;  // floats; weights are [rows, cols] row-major, biases rows x 1
+};
+
+struct Fit {
+  // config
+  int C, gh, gw, hw, bsz, Lf;
+  GridLevels grid;
+  size_t n_table;  // floats
+  // small-param layout (offsets in floats, multiples of 8)
+  Seg W1, b1, W2, b2, G, R1, rb1, R2, rb2, R3, rb3;
+  int n_small = 0;
+  // device memory
+  float *tp = nullptr, *tm = nullptr, *tv = nullptr, *tg = nullptr;
+  float *sp = nullptr, *sm = nullptr, *sv = nullptr, *sg = nullptr;
+  float* wsplit = nullptr;  // [2][n_small] TF32 hi / lo planes of the small params (x3 GEMM operands)
+  // activations: GEMM operands are stored as two fp32 planes (hi, lo), plane stride = bsz * ld
+  float *enc = nullptr, *h1 = nullptr, *dpred = nullptr, *dh1 = nullptr;
+  float *Fout = nullptr, *denc = nullptr;
+  float *rawb = nullptr, *r1 = nullptr, *r2 = nullptr, *dR = nullptr, *dr2 = nullptr, *dr1 = nullptr;
+  float* Rout = nullptr;
+  int ld_enc, ld_h1, ld_raw, ld_r;
+  // schedule
+  int num_iters = 0, freeze_step = 0;
+  int* idx = nullptr;         // [num_iters, bsz]
+  AdamScalars *sc_main = nullptr, *sc_res = nullptr;
+  float* losses = nullptr;    // [num_iters, 5]
+  int* step_base = nullptr;
+  float wd = 1e-5f, loss_scale = 1024.f;
+  // bank (borrowed)
+  const float* bank = nullptr;
+  const float* coords = nullptr;
+  size_t bank_rows = 0;
+  // graphs (captured on a stream owned by the engine: the caller's stream may be the legacy default stream,
+  // which cannot be captured)
+  cudaGraphExec_t graph1 = nullptr, graph2 = nullptr;
+  int graph_steps = 0;
+  long long graph1_nodes = 0, graph2_nodes = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // query workspace
+  int q_cap = 0;
+  float *q_enc = nullptr, *q_h1 = nullptr, *q_raw = nullptr, *q_r1 = nullptr, *q_r2 = nullptr;
+  float* q_stage = nullptr;
+  size_t q_stage_cap = 0;
+  std::vector<void*> owned;
+};
+
+static int fit_alloc(Fit* f, void** p, size_t bytes, bool zero = true) {
+  DVT_CUDA_OK(cudaMalloc(p, bytes));
+  f->owned.push_back(*p);
+  if (zero) DVT_CUDA_OK(cudaMemset(*p, 0, bytes));
+  return DVT_OK;
+}
+
+static int r8(int x) { return (x + 7) / 8 * 8; }
+
+int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const float* scale, const uint32_t* res,
+               const uint32_t* size, const uint32_t* offset, const uint32_t* hashed) {
+  DVT_REQUIRE(C % 32 == 0 && C >= 32 && C <= 1536, "fit: feat_dim %d unsupported (multiple of 32, <= 1536)", C);
+  DVT_REQUIRE(n_levels >= 1 && n_levels <= FIT_MAX_LEVELS, "fit: n_levels %d out of range", n_levels);
+  DVT_REQUIRE(bsz >= 8 && bsz % 8 == 0, "fit: pixel batch %d must be a positive multiple of 8", bsz);
+  DVT_REQUIRE(gh > 0 && gw > 0, "fit: bad noise-map size");
+  {
+    int prc = gemm_prepare();
+    if (prc) return prc;
+  }
+  Fit* f = new Fit();
+  DVT_CUDA_OK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+  DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_out, cudaEventDisableTiming));
+  f->C = C; f->gh = gh; f->gw = gw; f->hw = gh * gw; f->bsz = bsz; f->Lf = n_levels * FIT_F;
+  f->grid.n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    f->grid.scale[l] = scale[l]; f->grid.res[l] = res[l]; f->grid.size[l] = size[l];
+    f->grid.offset[l] = offset[l]; f->grid.hashed[l] = hashed[l];
+  }
+  f->grid.offset[n_levels] = offset[n_levels];
+  f->n_table = (size_t)offset[n_levels] * FIT_F;
+  int off = 0;
+  auto seg = [&](Seg& s, int rows, int cols) { s.off = off; s.rows = rows; s.cols = cols; off += r8(rows * cols); };
+  const int H1 = C / 2, Hr = C / 4;
+  seg(f->W1, H1, f->Lf); seg(f->b1, H1, 1); seg(f->W2, C, H1); seg(f->b2, C, 1);
+  seg(f->G, f->hw, C);
+  seg(f->R1, Hr, C); seg(f->rb1, Hr, 1); seg(f->R2, Hr, Hr); seg(f->rb2, Hr, 1); seg(f->R3, C, Hr); seg(f->rb3, C, 1);
+  f->n_small = off;
+  f->ld_enc = f->Lf + 8; f->ld_h1 = H1 + 8; f->ld_raw = C + 8; f->ld_r = Hr + 8;
+  int rc = 0;
+  auto A = [&](void** p, size_t bytes) { if (!rc) rc = fit_alloc(f, p, bytes); };
+  A((void**)&f->tp, f->n_table * 4); A((void**)&f->tm, f->n_table * 4); A((void**)&f->tv, f->n_table * 4);
+  A((void**)&f->tg, f->n_table * 4);
+  A((void**)&f->sp, (size_t)off * 4); A((void**)&f->sm, (size_t)off * 4); A((void**)&f->sv, (size_t)off * 4);
+  A((void**)&f->sg, (size_t)off * 4); A((void**)&f->wsplit, (size_t)off * 8);
+  const size_t n = bsz;
+  A((void**)&f->enc, n * f->ld_enc * 8); A((void**)&f->h1, n * f->ld_h1 * 8); A((void**)&f->dpred, n * C * 8);
+  A((void**)&f->dh1, n * H1 * 8); A((void**)&f->Fout, n * C * 4); A((void**)&f->denc, n * f->Lf * 4);
+  A((void**)&f->rawb, n * f->ld_raw * 8); A((void**)&f->r1, n * f->ld_r * 8); A((void**)&f->r2, n * f->ld_r * 8);
+  A((void**)&f->dR, n * C * 8); A((void**)&f->dr2, n * Hr * 8); A((void**)&f->dr1, n * Hr * 8);
+  A((void**)&f->Rout, n * C * 4); A((void**)&f->step_base, sizeof(int));
+  if (rc) { for (void* p : f->owned) cudaFree(p); delete f; return rc; }
+  // ones columns (bias gradients through the weight-gradient GEMMs)
+  const int tb = 256, nb = (bsz + tb - 1) / tb;
+  fit_fill_col_kernel<<<nb, tb>>>(f->enc, f->ld_enc, f->Lf, bsz, 1.f);
+  fit_fill_col_kernel<<<nb, tb>>>(f->h1, f->ld_h1, H1, bsz, 1.f);
+  fit_fill_col_kernel<<<nb, tb>>>(f->rawb, f->ld_raw, C, bsz, 1.f);
+  fit_fill_col_kernel<<<nb, tb>>>(f->r1, f->ld_r, Hr, bsz, 1.f);
+  fit_fill_col_kernel<<<nb, tb>>>(f->r2, f->ld_r, Hr, bsz, 1.f);
+  DVT_CUDA_OK(cudaDeviceSynchronize());
+  *out = f;
+  return DVT_OK;
+}
+
+static void fit_drop_graphs(Fit* f) {
+  if (f->graph1) cudaGraphExecDestroy(f->graph1);
+  if (f->graph2) cudaGraphExecDestroy(f->graph2);
+  f->graph1 = f->graph2 = nullptr;
+}
+
+void fit_destroy(Fit* f) {
+  if (!f) return;
+  fit_drop_graphs(f);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  if (f->ev_in) cudaEventDestroy(f->ev_in);
+  if (f->ev_out) cudaEventDestroy(f->ev_out);
+  for (void* p : f->owned) cudaFree(p);
+  cudaFree(f->idx); cudaFree(f->sc_main); cudaFree(f->sc_res); cudaFree(f->losses);
+  cudaFree(f->q_enc); cudaFree(f->q_h1); cudaFree(f->q_raw); cudaFree(f->q_r1); cudaFree(f->q_r2); cudaFree(f->q_stage);
+  delete f;
+}
+
+static bool fit_find(Fit* f, const std::string& name, Seg** s) {
+  struct { const char* n; Seg* s; } tab[] = {
+      {"mlp.0.weight", &f->W1}, {"mlp.0.bias", &f->b1}, {"mlp.2.weight", &f->W2}, {"mlp.2.bias", &f->b2},
+      {"G", &f->G}, {"res.0.weight", &f->R1}, {"res.0.bias", &f->rb1}, {"res.2.weight", &f->R2},
+      {"res.2.bias", &f->rb2}, {"res.4.weight", &f->R3}, {"res.4.bias", &f->rb3}};
+  for (auto& t : tab)
+    if (name == t.n) { *s = t.s; return true; }
+  return false;
+}
+
+static int fit_stage(Fit* f, size_t floats) {
+  if (f->q_stage_cap < floats) {
+    cudaFree(f->q_stage); f->q_stage = nullptr; f->q_stage_cap = 0;
+    DVT_CUDA_OK(cudaMalloc(&f->q_stage, floats * 4));
+    f->q_stage_cap = floats;
+  }
+  return DVT_OK;
+}
+
+// Parameter names follow oracle/fit.py::PARAM_ORDER ("G" is the reference's shared_artifacts [1, C, h, w]).
+int fit_set_param(Fit* f, const char* name_c, const float* src, size_t numel) {
+  const std::string name(name_c);
+  if (name == "table") {
+    DVT_REQUIRE(numel == f->n_table, "fit_set_param: table has %zu elements, expected %zu", numel, f->n_table);
+    DVT_CUDA_OK(cudaMemcpy(f->tp, src, numel * 4, cudaMemcpyDefault));
+    return DVT_OK;
+  }
+  Seg* s = nullptr;
+  DVT_REQUIRE(fit_find(f, name, &s), "fit_set_param: unknown parameter %s", name_c);
+  const size_t expect = (size_t)s->rows * s->cols;
+  DVT_REQUIRE(numel == expect, "fit_set_param: %s has %zu elements, expected %zu", name_c, numel, expect);
+  if (name == "G") {  // [C, h*w] -> [h*w, C]
+    int rc = fit_stage(f, numel);
+    if (rc) return rc;
+    DVT_CUDA_OK(cudaMemcpy(f->q_stage, src, numel * 4, cudaMemcpyDefault));
+    fit_transpose_kernel<<<256, 256>>>(f->q_stage, f->sp + s->off, f->C, f->hw);
+    DVT_CUDA_OK(cudaGetLastError());
+    DVT_CUDA_OK(cudaDeviceSynchronize());
+  } else {
+    DVT_CUDA_OK(cudaMemcpy(f->sp + s->off, src, numel * 4, cudaMemcpyDefault));
+  }
+  return DVT_OK;
+}
+
+int fit_get_param(Fit* f, const char* name_c, float* dst, size_t numel) {
+  const std::string name(name_c);
+  DVT_CUDA_OK(cudaDeviceSynchronize());
+  if (name == "table") {
+    DVT_REQUIRE(numel == f->n_table, "fit_get_param: table size mismatch");
+    DVT_CUDA_OK(cudaMemcpy(dst, f->tp, numel * 4, cudaMemcpyDefault));
+    return DVT_OK;
+  }
+  Seg* s = nullptr;
+  DVT_REQUIRE(fit_find(f, name, &s), "fit_get_param: unknown parameter %s", name_c);
+  DVT_REQUIRE(numel == (size_t)s->rows * s->cols, "fit_get_param: %s size mismatch", name_c);
+  if (name == "G") {
+    int rc = fit_stage(f, numel);
+    if (rc) return rc;
+    fit_transpose_kernel<<<256, 256>>>(f->sp + s->off, f->q_stage, f->hw, f->C);
+    DVT_CUDA_OK(cudaGetLastError());
+    DVT_CUDA_OK(cudaMemcpy(dst, f->q_stage, numel * 4, cudaMemcpyDefault));
+  } else {
+    DVT_CUDA_OK(cudaMemcpy(dst, f->sp + s->off, numel * 4, cudaMemcpyDefault));
+  }
+  return DVT_OK;
+}
+
+// Zeroes optimiser state / gradients, rebuilds the bf16 mirrors and installs the schedule of one fit.
+// idx_host: int32 [num_iters, bsz] bank rows (the np.random.randint stream, main_img_denoising.py:73).
+int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, const int* idx_host, int num_iters,
+              float lr, float min_lr, int warmup_iters, float freeze_after, float weight_decay, float loss_scale) {
+  DVT_REQUIRE(bank && coords && idx_host && num_iters > 0, "fit_begin: bad arguments");
+  DVT_REQUIRE(bank_rows % (size_t)f->hw == 0, "fit_begin: bank rows %zu not a multiple of h*w = %d", bank_rows, f->hw);
+  f->bank = bank; f->coords = coords; f->bank_rows = bank_rows;
+  f->wd = weight_decay; f->loss_scale = loss_scale;
+  // coordinates must lie in [0, 1] (assert of neural_feature_field.py:47, checked once per bank instead of per step)
+  int* bad = nullptr;
+  DVT_CUDA_OK(cudaMalloc(&bad, 4));
+  DVT_CUDA_OK(cudaMemset(bad, 0, 4));
+  fit_coord_range_kernel<<<256, 256>>>(coords, bank_rows * 2, bad);
+  int bad_h = 0;
+  DVT_CUDA_OK(cudaMemcpy(&bad_h, bad, 4, cudaMemcpyDeviceToHost));
+  cudaFree(bad);
+  DVT_REQUIRE(bad_h == 0, "coordinates should be in [0, 1]");
+  for (size_t i = 0; i < (size_t)num_iters * f->bsz; ++i)
+    DVT_REQUIRE(idx_host[i] >= 0 && (size_t)idx_host[i] < bank_rows, "fit_begin: index %d out of range at %zu",
+                idx_host[i], i);
+  if (num_iters != f->num_iters) {
+    cudaFree(f->idx); cudaFree(f->sc_main); cudaFree(f->sc_res); cudaFree(f->losses);
+    f->idx = nullptr; f->sc_main = f->sc_res = nullptr; f->losses = nullptr;
+    DVT_CUDA_OK(cudaMalloc(&f->idx, (size_t)num_iters * f->bsz * 4));
+    DVT_CUDA_OK(cudaMalloc(&f->sc_main, (size_t)num_iters * sizeof(AdamScalars)));
+    DVT_CUDA_OK(cudaMalloc(&f->sc_res, (size_t)num_iters * sizeof(AdamScalars)));
+    DVT_CUDA_OK(cudaMalloc(&f->losses, (size_t)num_iters * 5 * 4));
+    fit_drop_graphs(f);
+  }
+  const int freeze_step = (int)(freeze_after * num_iters);  // int(args.freeze_shared_artifacts_after * num_iters)
+  if (freeze_step != f->freeze_step) fit_drop_graphs(f);
+  f->num_iters = num_iters; f->freeze_step = freeze_step;
+  DVT_CUDA_OK(cudaMemcpy(f->idx, idx_host, (size_t)num_iters * f->bsz * 4, cudaMemcpyHostToDevice));
+  std::vector<AdamScalars> a(num_iters), b(num_iters);
+  for (int s = 0; s < num_iters; ++s) {
+    double lrs;  // dvt/utils/misc.py:306-322
+    if (s < warmup_iters) lrs = (double)lr * s / warmup_iters;
+    else lrs = min_lr + ((double)lr - min_lr) * 0.5 * (1.0 + cos(M_PI * (s - warmup_iters) / (double)(num_iters - warmup_iters)));
+    const int t = s + 1;
+    a[s].step_size = (float)(lrs / (1.0 - pow(0.9, t)));
+    a[s].bc2_sqrt = (float)sqrt(1.0 - pow(0.99, t));
+    const int tr = s - freeze_step;  // residual MLP: first update at s = freeze_step + 1 has t = 1
+    if (tr >= 1) {
+      b[s].step_size = (float)(lrs / (1.0 - pow(0.9, tr)));
+      b[s].bc2_sqrt = (float)sqrt(1.0 - pow(0.99, tr));
+    } else {
+      b[s].step_size = 0.f; b[s].bc2_sqrt = 1.f;
+    }
+  }
+  DVT_CUDA_OK(cudaMemcpy(f->sc_main, a.data(), a.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
+  DVT_CUDA_OK(cudaMemcpy(f->sc_res, b.data(), b.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
+  DVT_CUDA_OK(cudaMemset(f->losses, 0, (size_t)num_iters * 5 * 4));
+  DVT_CUDA_OK(cudaMemset(f->step_base, 0, 4));
+  DVT_CUDA_OK(cudaMemset(f->tm, 0, f->n_table * 4)); DVT_CUDA_OK(cudaMemset(f->tv, 0, f->n_table * 4));
+  DVT_CUDA_OK(cudaMemset(f->tg, 0, f->n_table * 4));
+  DVT_CUDA_OK(cudaMemset(f->sm, 0, (size_t)f->n_small * 4)); DVT_CUDA_OK(cudaMemset(f->sv, 0, (size_t)f->n_small * 4));
+  DVT_CUDA_OK(cudaMemset(f->sg, 0, (size_t)f->n_small * 4));
+  fit_split_kernel<<<256, 256>>>(f->sp, f->wsplit, (size_t)f->n_small);
+  DVT_CUDA_OK(cudaGetLastError());
+  DVT_CUDA_OK(cudaDeviceSynchronize());
+  return DVT_OK;
+}
+
+#define FIT_RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+// GEMM operands of the fit are fp32 hi/lo plane pairs; all products are 3xTF32 (fp32-accurate, gemm.cu "x3").
+struct Op {
+  const float* p;
+  int ld;
+  size_t plane;
+};
+
+// Y = act(X W^T + b):  X [M, K] planes, W [N, K] planes.  split_out: Y is written as hi/lo planes (feeds a GEMM).
+static int fit_linear(Op X, int M, int K, Op W, int N, const float* bias, int act, float* out, int ldo, size_t out_plane,
+                      bool split_out, cudaStream_t st, int impl) {
+  GemmEpi e;
+  e.bias = bias; e.act = act; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
+  e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
+  GemmShape s{M, N, K, 1};
+  s.x3 = 1; s.plane_a = X.plane; s.plane_b = W.plane;
+  return launch_gemm_tn(X.p, X.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
+}
+
+// dX = (dY . W) * (H > 0):  dY [M, Nout] K-major A; W stored [Nout, Kin] = MN-major B with N = Kin
+static int fit_dgrad(Op dY, int M, int Nout, Op W, int Kin, const float* Hmask, int ldmask, float* out, int ldo,
+                     size_t out_plane, bool split_out, cudaStream_t st, int impl) {
+  GemmEpi e;
+  e.mask_f32 = Hmask; e.ldmask = ldmask; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
+  e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
+  GemmShape s{M, Kin, Nout, 1};
+  s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = W.plane;
+  return launch_gemm_tn(dY.p, dY.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
+}
+
+// dW[Nout, Kin] (+ db[Nout]) += dY^T . [X | 1]:  dY stored [n, Nout] (MN-major A), X stored [n, Kin + ones] (MN-major B)
+static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb, cudaStream_t st, int impl) {
+  GemmEpi e;
+  e.out = gW; e.ldo = Kin; e.out_mode = OUT_F32_ATOMIC; e.last_col_out = gb;
+  int kb = (n + 31) / 32;
+  int splits = kb >= 64 ? 8 : kb >= 16 ? 4 : 1;
+  GemmShape s{Nout, Kin + 1, n, splits};
+  s.a_mn = 1; s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = X.plane;
+  return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
+}
+
+static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, int impl) {
+  const int n = f->bsz, C = f->C, H1 = C / 2, Hr = C / 4, Lf = f->Lf;
+  const StepRows sr{f->idx, f->step_base, step_off};
+  const int tb = 256;
+  const int enc_blocks = (n * f->grid.n_levels + tb - 1) / tb;
+  float* sp = f->sp; float* sg = f->sg;
+  const size_t wp = (size_t)f->n_small;  // weight plane stride
+  auto W = [&](const Seg& sgm) { return Op{f->wsplit + sgm.off, sgm.cols, wp}; };
+  const size_t p_enc = (size_t)n * f->ld_enc, p_h1 = (size_t)n * f->ld_h1, p_nc = (size_t)n * C, p_nh = (size_t)n * H1;
+  const size_t p_raw = (size_t)n * f->ld_raw, p_r = (size_t)n * f->ld_r, p_nr = (size_t)n * Hr;
+  const Op enc{f->enc, f->ld_enc, p_enc}, h1{f->h1, f->ld_h1, p_h1}, dpred{f->dpred, C, p_nc}, dh1{f->dh1, H1, p_nh};
+  const Op rawb{f->rawb, f->ld_raw, p_raw}, r1{f->r1, f->ld_r, p_r}, r2{f->r2, f->ld_r, p_r};
+  const Op dR{f->dR, C, p_nc}, dr2{f->dr2, Hr, p_nr}, dr1{f->dr1, Hr, p_nr};
+  // ---- forward ----
+  fit_encode_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->tp, f->coords, sr, n, f->enc, f->ld_enc, p_enc);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl));
+  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl));
+  if (phase2) {
+    fit_gather_rows_kernel<<<n, 192, 0, st>>>(f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw);
+    DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
+  count_launch();
+    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, st, impl));
+    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, st, impl));
+    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, st, impl));
+  }
+  // ---- loss + d pred ----
+  LossArgs la;
+  la.bank = f->bank; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
+  la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.plane = p_nc; la.gG = phase2 ? nullptr : sg + f->G.off;
+  la.losses = f->losses; la.n = n; la.C = C; la.hw = f->hw; la.loss_scale = f->loss_scale;
+  fit_loss_kernel<<<(n * 32 + tb - 1) / tb, tb, 0, st>>>(la);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  // ---- backward: field MLP + grid ----
+  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl));
+  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, st, impl));
+  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, st, impl));
+  FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl));
+  fit_grid_bwd_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->coords, sr, n, f->denc, Lf, f->tg);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  // ---- backward: residual MLP ----
+  if (phase2) {
+    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, st, impl));
+    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, st, impl));
+    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, st, impl));
+    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, st, impl));
+    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, st, impl));
+  }
+  // ---- Adam ----
+  fit_adam_table_kernel<<<num_sms() * 8, 256, 0, st>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv, (float4*)f->tg,
+                                                        f->n_table / 4, f->sc_main, f->step_base, step_off, f->wd);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  const int nv = f->n_small / 4;
+  fit_adam_small_kernel<<<(nv + 255) / 256, 256, 0, st>>>(
+      (float4*)f->sp, (float4*)f->sm, (float4*)f->sv, (float4*)f->sg, f->wsplit, nv, f->G.off / 4,
+      (f->G.off + r8(f->G.rows * f->G.cols)) / 4, f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res, f->step_base,
+      step_off, f->freeze_step, f->wd);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DVT_OK;
+}
+
+static int fit_capture(Fit* f, bool phase2, int steps, cudaStream_t st, int impl, cudaGraphExec_t* out, long long* nodes) {
+  cudaGraph_t graph = nullptr;
+  const long long before = launch_count();
+  DVT_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = DVT_OK;
+  for (int i = 0; i < steps && rc == DVT_OK; ++i) rc = fit_enqueue_step(f, i, phase2, st, impl);
+  if (rc == DVT_OK) {
+    fit_advance_kernel<<<1, 1, 0, st>>>(f->step_base, steps);
+    if (cudaGetLastError() != cudaSuccess) rc = DVT_ERR_CUDA;
+    count_launch();
+  }
+  *nodes = launch_count() - before;
+  count_launch(-*nodes);  // captured, not executed
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc != DVT_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  DVT_CUDA_OK(e);
+  e = cudaGraphInstantiate(out, graph, 0);
+  cudaGraphDestroy(graph);
+  DVT_CUDA_OK(e);
+  return DVT_OK;
+}
+
+// Runs steps [cur, cur + count) of the schedule installed by fit_begin.  use_graphs: 0 = plain launches,
+// k > 0 = CUDA graphs of k steps each (remainders and the phase boundary fall back to plain launches).
+int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
+  DVT_REQUIRE(f->bank && f->idx, "fit_run: call fit_begin first");
+  int cur = 0;
+  DVT_CUDA_OK(cudaMemcpyAsync(&cur, f->step_base, 4, cudaMemcpyDeviceToHost, caller));
+  DVT_CUDA_OK(cudaStreamSynchronize(caller));
+  // order the engine's stream after everything already enqueued on the caller's stream (the bank is produced there)
+  cudaStream_t st = f->stream;
+  DVT_CUDA_OK(cudaEventRecord(f->ev_in, caller));
+  DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev_in, 0));
+  DVT_REQUIRE(count >= 0 && cur + count <= f->num_iters, "fit_run: %d steps from %d exceed the schedule of %d", count, cur,
+              f->num_iters);
+  const int end = cur + count;
+  if (use_graphs > 0 && use_graphs != f->graph_steps) {
+    fit_drop_graphs(f);
+    f->graph_steps = use_graphs;
+  }
+  while (cur < end) {
+    const bool phase2 = cur > f->freeze_step;
+    // last step (exclusive) of the current phase within [cur, end)
+    const int phase_end = phase2 ? end : std::min(end, f->freeze_step + 1);
+    if (use_graphs > 0 && cur + use_graphs <= phase_end) {
+      cudaGraphExec_t* g = phase2 ? &f->graph2 : &f->graph1;
+      long long* nodes = phase2 ? &f->graph2_nodes : &f->graph1_nodes;
+      if (!*g) FIT_RC(fit_capture(f, phase2, use_graphs, st, impl, g, nodes));
+      DVT_CUDA_OK(cudaGraphLaunch(*g, st));
+      count_launch(*nodes);
+      cur += use_graphs;
+    } else {
+      FIT_RC(fit_enqueue_step(f, 0, phase2, st, impl));
+      fit_advance_kernel<<<1, 1, 0, st>>>(f->step_base, 1);
+      DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
+  count_launch();
+      cur += 1;
+    }
+  }
+  DVT_CUDA_OK(cudaEventRecord(f->ev_out, st));
+  DVT_CUDA_OK(cudaStreamWaitEvent(caller, f->ev_out, 0));
+  return DVT_OK;
+}
+
+int fit_losses(Fit* f, float* dst_host, int num_iters) {
+  DVT_REQUIRE(num_iters == f->num_iters, "fit_losses: schedule has %d steps", f->num_iters);
+  DVT_CUDA_OK(cudaDeviceSynchronize());
+  DVT_CUDA_OK(cudaMemcpy(dst_host, f->losses, (size_t)num_iters * 5 * 4, cudaMemcpyDeviceToHost));
+  return DVT_OK;
+}
+
+static int fit_query_reserve(Fit* f, int n) {
+  if (n <= f->q_cap) return DVT_OK;
+  cudaFree(f->q_enc); cudaFree(f->q_h1); cudaFree(f->q_raw); cudaFree(f->q_r1); cudaFree(f->q_r2);
+  f->q_enc = f->q_h1 = f->q_raw = f->q_r1 = f->q_r2 = nullptr; f->q_cap = 0;
+  DVT_CUDA_OK(cudaMalloc(&f->q_enc, (size_t)n * f->ld_enc * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_h1, (size_t)n * f->ld_h1 * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_raw, (size_t)n * f->ld_raw * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_r1, (size_t)n * f->ld_r * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_r2, (size_t)n * f->ld_r * 8));
+  f->q_cap = n;
+  return DVT_OK;
+}
+
+// denoised_feats = field(coords): NeuralFeatureField.forward on n points (final query, main_img_denoising.py:121-130)
+int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, int impl) {
+  DVT_REQUIRE(coords && out && n > 0, "fit_query: bad arguments");
+  FIT_RC(fit_query_reserve(f, n));
+  const int C = f->C, H1 = C / 2;
+  const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
+  const StepRows sr{nullptr, f->step_base, 0};
+  fit_encode_kernel<<<(n * f->grid.n_levels + 255) / 256, 256, 0, st>>>(f->grid, f->tp, coords, sr, n, f->q_enc, f->ld_enc,
+                                                                       cap * f->ld_enc);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  FIT_RC(fit_linear(Op{f->q_enc, f->ld_enc, cap * f->ld_enc}, n, f->Lf, Op{f->wsplit + f->W1.off, f->Lf, wp}, H1,
+                    f->sp + f->b1.off, ACT_RELU, f->q_h1, f->ld_h1, cap * f->ld_h1, true, st, impl));
+  FIT_RC(fit_linear(Op{f->q_h1, f->ld_h1, cap * f->ld_h1}, n, H1, Op{f->wsplit + f->W2.off, H1, wp}, C, f->sp + f->b2.off,
+                    ACT_NONE, out, C, 0, false, st, impl));
+  return DVT_OK;
+}
+
+// pred_residual = residual_predictor(raw) on n rows (offline_denoiser.py:40-46,105)
+int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, int impl) {
+  DVT_REQUIRE(raw && out && n > 0, "fit_residual: bad arguments");
+  FIT_RC(fit_query_reserve(f, n));
+  const int C = f->C, Hr = C / 4;
+  const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
+  const StepRows sr{nullptr, f->step_base, 0};
+  fit_gather_rows_kernel<<<n, 192, 0, st>>>(raw, C, sr, n, f->q_raw, f->ld_raw, cap * f->ld_raw);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  FIT_RC(fit_linear(Op{f->q_raw, f->ld_raw, cap * f->ld_raw}, n, C, Op{f->wsplit + f->R1.off, C, wp}, Hr, f->sp + f->rb1.off,
+                    ACT_RELU, f->q_r1, f->ld_r, cap * f->ld_r, true, st, impl));
+  FIT_RC(fit_linear(Op{f->q_r1, f->ld_r, cap * f->ld_r}, n, Hr, Op{f->wsplit + f->R2.off, Hr, wp}, Hr, f->sp + f->rb2.off,
+                    ACT_RELU, f->q_r2, f->ld_r, cap * f->ld_r, true, st, impl));
+  FIT_RC(fit_linear(Op{f->q_r2, f->ld_r, cap * f->ld_r}, n, Hr, Op{f->wsplit + f->R3.off, Hr, wp}, C, f->sp + f->rb3.off,
+                    ACT_NONE, out, C, 0, false, st, impl));
+  return DVT_OK;
+}
+
+// unit-test entry points ---------------------------------------------------------------------------------
+static int levels_from_arrays(GridLevels* g, int n_levels, const float* scale, const uint32_t* res, const uint32_t* size,
+                              const uint32_t* offset, const uint32_t* hashed) {
+  DVT_REQUIRE(n_levels >= 1 && n_levels <= FIT_MAX_LEVELS, "hashgrid: n_levels %d out of range", n_levels);
+  g->n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    g->scale[l] = scale[l]; g->res[l] = res[l]; g->size[l] = size[l]; g->offset[l] = offset[l]; g->hashed[l] = hashed[l];
+  }
+  g->offset[n_levels] = offset[n_levels];
+  return DVT_OK;
+}
+
+int hashgrid_corners(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
+                     const uint32_t* hashed, const float* coords, int n, uint32_t* idx, float* w, cudaStream_t st) {
+  GridLevels g;
+  FIT_RC(levels_from_arrays(&g, n_levels, scale, res, size, offset, hashed));
+  fit_corners_kernel<<<(n * n_levels + 255) / 256, 256, 0, st>>>(g, coords, n, idx, w);
+  DVT_CUDA_OK(cudaGetLastError());
+  return DVT_OK;
+}
+
+int hashgrid_fwd(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
+                 const uint32_t* hashed, const float* table, const float* coords, int n, float* out, cudaStream_t st) {
+  GridLevels g;
+  FIT_RC(levels_from_arrays(&g, n_levels, scale, res, size, offset, hashed));
+  fit_encode_f32_kernel<<<(n * n_levels + 255) / 256, 256, 0, st>>>(g, table, coords, n, out);
+  DVT_CUDA_OK(cudaGetLastError());
+  return DVT_OK;
+}
+
+int hashgrid_bwd(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
+                 const uint32_t* hashed, const float* coords, int n, const float* dout, float* gtable, cudaStream_t st) {
+  GridLevels g;
+  FIT_RC(levels_from_arrays(&g, n_levels, scale, res, size, offset, hashed));
+  const StepRows sr{nullptr, nullptr, 0};
+  fit_grid_bwd_kernel<<<(n * n_levels + 255) / 256, 256, 0, st>>>(g, coords, sr, n, dout, n_levels * FIT_F, gtable);
+  DVT_CUDA_OK(cudaGetLastError());
+  return DVT_OK;
+}
+
+int fit_n_small(const Fit* f) { return f->n_small; }
+size_t fit_n_table(const Fit* f) { return f->n_table; }
+
+}  // namespace dvt

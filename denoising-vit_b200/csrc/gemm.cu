@@ -23,10 +23,10 @@ constexpr int NUM_EPI_WARPS = 4;
 constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int SCR_PITCH = 36;  // floats; 16B-aligned rows, conflict-free for the access pattern below
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool X3 = false>
 struct GemmSmem {
-  static constexpr int A_BYTES = BM * KB_BYTES;
-  static constexpr int B_BYTES = BN * KB_BYTES;
+  static constexpr int A_BYTES = BM * KB_BYTES * (X3 ? 2 : 1);  // x3: hi plane then lo plane
+  static constexpr int B_BYTES = BN * KB_BYTES * (X3 ? 2 : 1);
   static constexpr int SCR_BYTES = NUM_EPI_WARPS * 32 * SCR_PITCH * 4;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
@@ -37,11 +37,13 @@ struct GemmSmem {
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES, bool TF32>
+template <int BN, int STAGES, bool TF32, bool A_MN, bool B_MN, bool X3 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape s,
                   GemmEpi e) {
-  using L = GemmSmem<BN, STAGES>;
+  static_assert(!X3 || TF32, "x3 is a TF32 mode");
+  static_assert(X3 || !(TF32 && (A_MN || B_MN)), "plain TF32 is K-major only");
+  using L = GemmSmem<BN, STAGES, X3>;
   constexpr int ELEM = TF32 ? 4 : 2;
   constexpr int BK = KB_BYTES / ELEM;         // elements of K per stage
   constexpr int UMMA_K_BYTES = 32;            // K=16 bf16 or K=8 tf32 per instruction
@@ -108,8 +110,39 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           mbar_expect_tx(&full[stage], L::A_BYTES + L::B_BYTES);
-          tma_load_2d(sA + stage * L::A_BYTES, &tmA, &full[stage], kb * BK, tm * BM);
-          tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], kb * BK, tn * BN);
+          if (X3) {
+            // fp32 hi/lo planes: 3-D maps (inner, rows, plane); one box brings both planes of a tile / atom
+            if (A_MN) {
+#pragma unroll
+              for (int a = 0; a < BM / 32; ++a)
+                tma_load_3d(sA + stage * L::A_BYTES + a * 8192, &tmA, &full[stage], tm * BM + a * 32, kb * BK, 0);
+            } else {
+              tma_load_3d(sA + stage * L::A_BYTES, &tmA, &full[stage], kb * BK, tm * BM, 0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int a = 0; a < BN / 32; ++a)
+                tma_load_3d(sB + stage * L::B_BYTES + a * 8192, &tmB, &full[stage], tn * BN + a * 32, kb * BK, 0);
+            } else {
+              tma_load_3d(sB + stage * L::B_BYTES, &tmB, &full[stage], kb * BK, tn * BN, 0);
+            }
+          } else {
+            if (A_MN) {
+              // stored [K, M]: boxes of 64 (M, contiguous) x BK (K rows) = one MN-major swizzle-atom column each
+#pragma unroll
+              for (int a = 0; a < BM / 64; ++a)
+                tma_load_2d(sA + stage * L::A_BYTES + a * (BK * 128), &tmA, &full[stage], tm * BM + a * 64, kb * BK);
+            } else {
+              tma_load_2d(sA + stage * L::A_BYTES, &tmA, &full[stage], kb * BK, tm * BM);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a)
+                tma_load_2d(sB + stage * L::B_BYTES + a * (BK * 128), &tmB, &full[stage], tn * BN + a * 64, kb * BK);
+            } else {
+              tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], kb * BK, tn * BN);
+            }
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -120,7 +153,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, BM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -135,13 +168,38 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(sA + stage * L::A_BYTES), 0, 1024, 2);
-          const uint64_t db = make_smem_desc(smem_u32(sB + stage * L::B_BYTES), 0, 1024, 2);
+          // K-major: rows of 128 B (one swizzle atom of K), 8-row groups 1024 B apart; K advances 32 B per MMA.
+          // MN-major (bf16): tile = [MN/64 atoms][BK k-rows][64 mn]; atoms BK*128 B apart (LBO), 8-k groups 1024 B
+          // apart (SBO); K advances 16 rows = 2048 B per MMA.
+          // x3 (fp32 hi/lo planes): K-major tile = [plane][rows][128 B]; MN-major tile = [MN/32 atoms][plane][32 k-rows]
+          // [32 mn] (atoms 8192 B apart, lo plane +4096 B, K advances 8 rows = 1024 B per MMA).  MN-major TF32 operands
+          // must use the "128B swizzle with 32B atoms" layout (descriptor layout type 1, TMA SWIZZLE_128B_ATOM_32B):
+          // the swizzle pattern repeats every 4 K-rows, so the stride between K groups (SBO) is 512 B.
+          const uint32_t a_base = smem_u32(sA + stage * L::A_BYTES), b_base = smem_u32(sB + stage * L::B_BYTES);
+          if (X3) {
+            const uint32_t a_lo = a_base + (A_MN ? 4096 : BM * KB_BYTES), b_lo = b_base + (B_MN ? 4096 : BN * KB_BYTES);
+            const uint32_t lbo_a = A_MN ? 8192 : 0, lbo_b = B_MN ? 8192 : 0;
 #pragma unroll
-          for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-            if (TF32) umma_tf32(d_tmem, da + adv, db + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_f16(d_tmem, da + adv, db + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+              const uint32_t ka = A_MN ? k * 1024 : k * UMMA_K_BYTES, kbb = B_MN ? k * 1024 : k * UMMA_K_BYTES;
+              constexpr uint32_t sbo_a = A_MN ? 512 : 1024, sbo_b = B_MN ? 512 : 1024;
+              constexpr uint32_t lt_a = A_MN ? 1 : 2, lt_b = B_MN ? 1 : 2;
+              const uint64_t dah = make_smem_desc(a_base + ka, lbo_a, sbo_a, lt_a), dal = make_smem_desc(a_lo + ka, lbo_a, sbo_a, lt_a);
+              const uint64_t dbh = make_smem_desc(b_base + kbb, lbo_b, sbo_b, lt_b), dbl = make_smem_desc(b_lo + kbb, lbo_b, sbo_b, lt_b);
+              umma_tf32(d_tmem, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);  // small terms first
+              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            }
+          } else {
+            const uint64_t da = make_smem_desc(a_base, A_MN ? BK * 128 : 0, 1024, 2);
+            const uint64_t db = make_smem_desc(b_base, B_MN ? BK * 128 : 0, 1024, 2);
+#pragma unroll
+            for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+              const uint64_t adv_a = (uint64_t)((A_MN ? k * 2048 : k * UMMA_K_BYTES) >> 4);
+              const uint64_t adv_b = (uint64_t)((B_MN ? k * 2048 : k * UMMA_K_BYTES) >> 4);
+              if (TF32) umma_tf32(d_tmem, da + adv_a, db + adv_b, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_f16(d_tmem, da + adv_a, db + adv_b, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) {
@@ -272,9 +330,11 @@ __global__ void gemm_tn_simt_kernel(const T* __restrict__ A, int lda, const T* _
   float acc = 0.0f;
   for (int k0 = 0; k0 < s.K; k0 += 16) {
     int ka = k0 + tx;
-    sa[ty][tx] = (m < s.M && ka < s.K) ? ld_as_float(A + (size_t)m * lda + ka) : 0.0f;
+    const T* ap = s.a_mn ? A + (size_t)ka * lda + m : A + (size_t)m * lda + ka;
+    sa[ty][tx] = (m < s.M && ka < s.K) ? ld_as_float(ap) + (s.x3 ? ld_as_float(ap + s.plane_a) : 0.0f) : 0.0f;
     int nb = blockIdx.x * 16 + ty;
-    sb[ty][tx] = (nb < s.N && ka < s.K) ? ld_as_float(B + (size_t)nb * ldb + ka) : 0.0f;
+    const T* bp = s.b_mn ? B + (size_t)ka * ldb + nb : B + (size_t)nb * ldb + ka;
+    sb[ty][tx] = (nb < s.N && ka < s.K) ? ld_as_float(bp) + (s.x3 ? ld_as_float(bp + s.plane_b) : 0.0f) : 0.0f;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
@@ -287,24 +347,47 @@ __global__ void gemm_tn_simt_kernel(const T* __restrict__ A, int lda, const T* _
   }
 }
 
-template <int BN, int STAGES, bool TF32>
+template <int BN, int STAGES, bool TF32, bool A_MN, bool B_MN, bool X3 = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const GemmEpi& e,
               cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
-  auto kern = gemm_tn_tc_kernel<BN, STAGES, TF32>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DVT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  using L = GemmSmem<BN, STAGES, X3>;
+  auto kern = gemm_tn_tc_kernel<BN, STAGES, TF32, A_MN, B_MN, X3>;
   const int tiles = ((s.M + BM - 1) / BM) * ((s.N + BN - 1) / BN) * s.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, s, e);
+  count_launch();
   DVT_CUDA_OK(cudaGetLastError());
   return DVT_OK;
 }
 
+template <int BN, int STAGES, bool TF32, bool A_MN, bool B_MN, bool X3 = false>
+int prep_one() {
+  DVT_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<BN, STAGES, TF32, A_MN, B_MN, X3>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, STAGES, X3>::TOTAL));
+  return DVT_OK;
+}
+
 }  // namespace
+
+// Opts every instantiation into its dynamic shared memory size.  Called once, outside any stream capture.
+int gemm_prepare() {
+  static bool done = false;
+  if (done) return DVT_OK;
+  int rc;
+  if ((rc = prep_one<256, 4, true, false, false>())) return rc;
+  if ((rc = prep_one<128, 6, true, false, false>())) return rc;
+  if ((rc = prep_one<256, 4, false, true, true>())) return rc;
+  if ((rc = prep_one<128, 6, false, true, true>())) return rc;
+  if ((rc = prep_one<256, 4, false, false, true>())) return rc;
+  if ((rc = prep_one<128, 6, false, false, true>())) return rc;
+  if ((rc = prep_one<256, 4, false, false, false>())) return rc;
+  if ((rc = prep_one<128, 6, false, false, false>())) return rc;
+  if ((rc = prep_one<128, 3, true, false, false, true>())) return rc;
+  if ((rc = prep_one<128, 3, true, false, true, true>())) return rc;
+  if ((rc = prep_one<128, 3, true, true, true, true>())) return rc;
+  done = true;
+  return DVT_OK;
+}
 
 int default_gemm_impl() {
   static int impl = -1;
@@ -316,13 +399,18 @@ int default_gemm_impl() {
 }
 
 int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dtype, const GemmShape& shape,
-                   const GemmEpi& epi, cudaStream_t stream, int impl) {
+                   const GemmEpi& epi_in, cudaStream_t stream, int impl) {
   if (impl < 0) impl = default_gemm_impl();
   GemmShape s = shape;
+  GemmEpi epi = epi_in;
   if (s.splits < 1) s.splits = 1;
   DVT_REQUIRE(s.M > 0 && s.N > 0 && s.K > 0, "gemm: empty shape M=%d N=%d K=%d", s.M, s.N, s.K);
   DVT_REQUIRE(s.splits == 1 || epi.out_mode == OUT_F32_ATOMIC, "gemm: split-K needs OUT_F32_ATOMIC");
   DVT_REQUIRE(epi.out == nullptr || epi.ldo % 4 == 0, "gemm: ldo must be a multiple of 4 (got %d)", epi.ldo);
+  DVT_REQUIRE(epi.last_col_out == nullptr || epi.out_mode == OUT_F32_ATOMIC, "gemm: last_col_out needs OUT_F32_ATOMIC");
+  epi.last_col_n = epi.last_col_out ? s.N - 1 : -1;
+  // the vector post-stage must not straddle the redirected column: keep N-1 in a scalar tail
+  DVT_REQUIRE(epi.last_col_out == nullptr || (s.N - 1) % 4 == 0, "gemm: last_col_out needs (N-1) %% 4 == 0 (N=%d)", s.N);
 
   if (impl == GEMM_SIMT_DEBUG) {
     dim3 grid((s.N + 15) / 16, (s.M + 15) / 16), block(16, 16);
@@ -333,11 +421,35 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
       gemm_tn_simt_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(A), lda,
                                                              reinterpret_cast<const float*>(B), ldb, s, epi);
     DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
     return DVT_OK;
   }
 
+  {
+    int prc = gemm_prepare();
+    if (prc) return prc;
+  }
   const int elem = dtype == TMAP_BF16 ? 2 : 4;
   const int bk = KB_BYTES / elem;
+  if (s.x3) {
+    DVT_REQUIRE(dtype == TMAP_F32, "gemm: x3 needs fp32 operands");
+    DVT_REQUIRE(!(s.a_mn && !s.b_mn), "gemm: A MN-major with B K-major is not instantiated");
+    DVT_REQUIRE((lda * 4) % 16 == 0 && (ldb * 4) % 16 == 0 && (s.plane_a * 4) % 16 == 0 && (s.plane_b * 4) % 16 == 0,
+                "gemm: x3 pitches must be multiples of 16 bytes");
+    CUtensorMap tA, tB;
+    int rc3;
+    if (s.a_mn) rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.M, (uint64_t)s.K, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, 32, 2, true);
+    else rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.K, (uint64_t)s.M, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, BM, 2);
+    if (rc3) return rc3;
+    if (s.b_mn) rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.N, (uint64_t)s.K, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 32, 2, true);
+    else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 128, 2);
+    if (rc3) return rc3;
+    if (s.a_mn) return launch_tc<128, 3, true, true, true, true>(tA, tB, s, epi, stream);
+    if (s.b_mn) return launch_tc<128, 3, true, false, true, true>(tA, tB, s, epi, stream);
+    return launch_tc<128, 3, true, false, false, true>(tA, tB, s, epi, stream);
+  }
+  DVT_REQUIRE(dtype == TMAP_BF16 || (!s.a_mn && !s.b_mn), "gemm: MN-major operands are implemented for bf16 only");
+  DVT_REQUIRE(!(s.a_mn && !s.b_mn), "gemm: A MN-major with B K-major is not instantiated");
   DVT_REQUIRE((lda * elem) % 16 == 0 && (ldb * elem) % 16 == 0,
               "gemm: row pitch must be a multiple of 16 bytes (lda=%d ldb=%d elem=%d)", lda, ldb, elem);
   DVT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
@@ -345,15 +457,24 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
   // wide tiles when N is large enough to fill them; narrow ones for the small fit GEMMs
   const bool wide = s.N >= 256 && (s.N % 256 == 0 || s.N > 1024);
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d(&tmA, A, dtype, (uint64_t)s.M, (uint64_t)s.K, (uint64_t)lda * elem, BM, bk);
+  int rc;
+  if (s.a_mn) rc = make_tmap_2d(&tmA, A, dtype, (uint64_t)s.K, (uint64_t)s.M, (uint64_t)lda * elem, bk, 64);
+  else rc = make_tmap_2d(&tmA, A, dtype, (uint64_t)s.M, (uint64_t)s.K, (uint64_t)lda * elem, BM, bk);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, B, dtype, (uint64_t)s.N, (uint64_t)s.K, (uint64_t)ldb * elem, wide ? 256 : 128, bk);
+  if (s.b_mn) rc = make_tmap_2d(&tmB, B, dtype, (uint64_t)s.K, (uint64_t)s.N, (uint64_t)ldb * elem, bk, 64);
+  else rc = make_tmap_2d(&tmB, B, dtype, (uint64_t)s.N, (uint64_t)s.K, (uint64_t)ldb * elem, wide ? 256 : 128, bk);
   if (rc) return rc;
-  if (dtype == TMAP_BF16) {
-    return wide ? launch_tc<256, 4, false>(tmA, tmB, s, epi, stream) : launch_tc<128, 6, false>(tmA, tmB, s, epi, stream);
-  } else {
-    return wide ? launch_tc<256, 4, true>(tmA, tmB, s, epi, stream) : launch_tc<128, 6, true>(tmA, tmB, s, epi, stream);
-  }
+  if (dtype == TMAP_F32)
+    return wide ? launch_tc<256, 4, true, false, false>(tmA, tmB, s, epi, stream)
+                : launch_tc<128, 6, true, false, false>(tmA, tmB, s, epi, stream);
+  if (s.a_mn)
+    return wide ? launch_tc<256, 4, false, true, true>(tmA, tmB, s, epi, stream)
+                : launch_tc<128, 6, false, true, true>(tmA, tmB, s, epi, stream);
+  if (s.b_mn)
+    return wide ? launch_tc<256, 4, false, false, true>(tmA, tmB, s, epi, stream)
+                : launch_tc<128, 6, false, false, true>(tmA, tmB, s, epi, stream);
+  return wide ? launch_tc<256, 4, false, false, false>(tmA, tmB, s, epi, stream)
+              : launch_tc<128, 6, false, false, false>(tmA, tmB, s, epi, stream);
 }
 
 }  // namespace dvt

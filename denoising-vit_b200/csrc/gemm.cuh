@@ -12,13 +12,18 @@ enum GemmOut {
   OUT_F32_ATOMIC = 2,  // out[m, n] += v                    (fp32 atomics; split-K partial sums)
   OUT_F32_RESID = 3,   // out[m, n] += gamma[n] * v         (fp32 residual stream, in place; gamma may be null)
   OUT_F32_REMAP = 4,   // out[remap(m), n] = v + addend[m % rows_per_group, n]   (patch-embed -> token rows)
+  OUT_F32_SPLIT = 5,   // out[m, n] = tf32_hi(v), out[out_plane + m*ldo + n] = v - tf32_hi(v)   (operand of an x3 GEMM)
 };
+
+// fp32 value -> (hi, lo) with hi exactly representable in TF32 (low 13 mantissa bits zero) and hi + lo == v exactly
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 struct GemmEpi {
   // pre-stage (per element, thread-per-row registers)
   const float* bias = nullptr;        // [N] added to the accumulator
   int act = ACT_NONE;                 // activation applied after bias
   const __nv_bfloat16* mask = nullptr;  // optional [M, ldmask]: v *= (mask[m, n] > 0)   (ReLU backward)
+  const float* mask_f32 = nullptr;      // same, fp32 mask tensor
   int ldmask = 0;
   float alpha = 1.0f;                 // v *= alpha (after activation / mask)
   __nv_bfloat16* out_t = nullptr;     // optional transposed bf16 copy: out_t[n, m], leading dim ldt
@@ -27,6 +32,10 @@ struct GemmEpi {
   int out_mode = OUT_BF16;
   void* out = nullptr;
   int ldo = 0;
+  size_t out_plane = 0;               // OUT_F32_SPLIT: element offset of the lo plane
+  int last_col_n = -1;                // = N-1 when last_col_out is set (filled in by launch_gemm)
+  float* last_col_out = nullptr;      // OUT_F32_ATOMIC only: column N-1 is accumulated into last_col_out[m] instead
+                                      // (bias gradient through a ones column in the B operand)
   const float* gamma = nullptr;       // LayerScale (OUT_F32_RESID)
   const float* addend = nullptr;      // [rows_per_group, N] (OUT_F32_REMAP)
   int rows_per_group = 0;             // patches per image
@@ -36,7 +45,14 @@ struct GemmEpi {
 
 struct GemmShape {
   int M, N, K;
-  int splits;  // split-K factor (>1 requires OUT_F32_ATOMIC)
+  int splits;    // split-K factor (>1 requires OUT_F32_ATOMIC)
+  int a_mn = 0;  // 0: A is [M, K] row-major (K contiguous);  1: A is stored as [K, M] row-major (M contiguous)
+  int b_mn = 0;  // 0: B is [N, K] row-major (K contiguous);  1: B is stored as [K, N] row-major (N contiguous)
+  // 3xTF32 ("x3"): fp32-accurate product on the tensor cores.  Each fp32 operand is stored as two planes
+  // (hi = TF32-exact part at the base pointer, lo = remainder at base + plane elements) and the kernel accumulates
+  // A_hi.B_hi + A_hi.B_lo + A_lo.B_hi.
+  int x3 = 0;
+  size_t plane_a = 0, plane_b = 0;
 };
 
 __device__ __forceinline__ float epi_pre(const GemmEpi& e, int m, int n, float acc) {
@@ -48,6 +64,7 @@ __device__ __forceinline__ float epi_pre(const GemmEpi& e, int m, int n, float a
     float h = __bfloat162float(e.mask[(size_t)m * e.ldmask + n]);
     v = h > 0.0f ? v : 0.0f;
   }
+  if (e.mask_f32) v = e.mask_f32[(size_t)m * e.ldmask + n] > 0.0f ? v : 0.0f;
   return v * e.alpha;
 }
 
@@ -71,7 +88,8 @@ __device__ __forceinline__ void epi_post1(const GemmEpi& e, int m, int n, float 
       reinterpret_cast<float*>(e.out)[row * e.ldo + n] = v;
       break;
     case OUT_F32_ATOMIC:
-      atomicAdd(reinterpret_cast<float*>(e.out) + row * e.ldo + n, v);
+      if (e.last_col_out && n == e.last_col_n) atomicAdd(e.last_col_out + m, v);
+      else atomicAdd(reinterpret_cast<float*>(e.out) + row * e.ldo + n, v);
       break;
     case OUT_F32_RESID: {
       float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + n;
@@ -82,6 +100,12 @@ __device__ __forceinline__ void epi_post1(const GemmEpi& e, int m, int n, float 
       int p = m % e.rows_per_group;
       float a = e.addend ? __ldg(e.addend + (size_t)p * e.ldo + n) : 0.0f;
       reinterpret_cast<float*>(e.out)[row * e.ldo + n] = v + a;
+    } break;
+    case OUT_F32_SPLIT: {
+      float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + n;
+      const float hi = tf32_hi(v);
+      o[0] = hi;
+      o[e.out_plane] = v - hi;
     } break;
   }
 }
@@ -101,10 +125,8 @@ __device__ __forceinline__ void epi_post4(const GemmEpi& e, int m, int n, float4
       break;
     case OUT_F32_ATOMIC: {
       float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + n;
-      atomicAdd(o + 0, v.x);
-      atomicAdd(o + 1, v.y);
-      atomicAdd(o + 2, v.z);
-      atomicAdd(o + 3, v.w);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
     } break;
     case OUT_F32_RESID: {
       float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + row * e.ldo + n);
@@ -126,16 +148,23 @@ __device__ __forceinline__ void epi_post4(const GemmEpi& e, int m, int n, float4
       v.w += a.w;
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + row * e.ldo + n) = v;
     } break;
+    case OUT_F32_SPLIT: {
+      float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + n;
+      const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      *reinterpret_cast<float4*>(o) = hi;
+      *reinterpret_cast<float4*>(o + e.out_plane) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    } break;
   }
 }
 
 enum GemmImpl { GEMM_TCGEN05 = 0, GEMM_SIMT_DEBUG = 1 };
 
-// dtype: TMAP_BF16 (kind::f16, bf16 operands) or TMAP_F32 (kind::tf32, fp32 operands).
-// lda / ldb in elements.  Both A and B are row-major with K contiguous.
+// dtype: TMAP_BF16 (kind::f16, bf16 operands) or TMAP_F32 (kind::tf32, fp32 operands; K-major only).
+// lda / ldb: row pitch in elements of the stored matrix ([M,K] / [N,K], or [K,M] / [K,N] for MN-major operands).
 int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dtype, const GemmShape& shape,
                    const GemmEpi& epi, cudaStream_t stream, int impl = -1 /* -1: process default */);
 
 int default_gemm_impl();
+int gemm_prepare();
 
 }  // namespace dvt

@@ -28,6 +28,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return DVT_ERR_CUDA;
 }
 
+static long long g_launches = 0;
+void count_launch(long long n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -56,7 +60,7 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* out, const void* base, TmapDtype dt, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box) {
+                  const cuuint64_t* strides, const cuuint32_t* box, bool swizzle_atom32 = false) {
   EncodeTiledFn fn = get_encode();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -65,7 +69,9 @@ static int encode(CUtensorMap* out, const void* base, TmapDtype dt, int rank, co
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMapDataType cdt = dt == TMAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, cdt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u pitch %llu)",
@@ -85,11 +91,12 @@ int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t rows
 }
 
 int make_tmap_3d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                 bool swizzle_atom32) {
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-  cuuint32_t box[3] = {box0, box1, 1};
-  return encode(out, base, dt, 3, dims, strides, box);
+  cuuint32_t box[3] = {box0, box1, box2};
+  return encode(out, base, dt, 3, dims, strides, box, swizzle_atom32);
 }
 
 }  // namespace dvt

@@ -203,6 +203,7 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
   }
   prefix_rows_kernel<<<B * v->prefix, 256, 0, stream>>>(prefix_rows, v->x, B, v->prefix, ntok, C);
   DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
 
   const int Mi = (int)M;
   for (int i = 0; i <= layer_index; ++i) {
@@ -239,6 +240,7 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
       fc2_k = v->mlp_hidden / 2;
       swiglu_kernel<<<num_sms() * 8, 256, 0, stream>>>(v->hid, v->hid2, M, fc2_k);
       DVT_CUDA_OK(cudaGetLastError());
+      count_launch();
       fc2_in = v->hid2;
     }
     {
@@ -256,6 +258,7 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
   } else {
     strip_copy_kernel<<<Mi, 256, 0, stream>>>(v->x, C, out, C, Mi, C, ntok, skip);
     DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
   }
   return DVT_OK;
 }

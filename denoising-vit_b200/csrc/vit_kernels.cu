@@ -86,6 +86,7 @@ int launch_layernorm(const float* x, int ldx, const float* gamma, const float* b
     layernorm_kernel<float><<<blocks, threads, 0, stream>>>(x, ldx, gamma, beta, (float*)y, ldy, rows, C, eps,
                                                             in_group > 0 ? in_group : 1, skip);
   DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
   return DVT_OK;
 }
 
@@ -139,6 +140,7 @@ int launch_im2col(const void* x, bool x_bf16, __nv_bfloat16* out, int B, int H, 
   else
     im2col_kernel<float><<<blocks, threads, 0, stream>>>((const float*)x, out, B, H, W, P, S, h, w, Kp);
   DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
   return DVT_OK;
 }
 

@@ -21,6 +21,7 @@ SIGNATURES = {
     "dvt_last_error": (c_char_p, []),
     "dvt_device_error": (c_int, [POINTER(c_uint)]),
     "dvt_set_debug_impl": (c_int, [c_int]),
+    "dvt_launch_count": (ctypes.c_longlong, []),
     "dvt_gemm_tn": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                             c_int, c_int, c_int, c_void_p]),
     "dvt_gemm_tn_residual": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -29,6 +30,27 @@ SIGNATURES = {
                               c_int, c_void_p]),
     "dvt_attention_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "dvt_im2col": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dvt_gemm_bf16_ex": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                 c_int, c_int, c_void_p, c_void_p]),
+    "dvt_gemm_f32x3": (c_int, [c_void_p, c_int, c_size_t, c_int, c_void_p, c_int, c_size_t, c_int, c_int, c_int, c_int,
+                               c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dvt_hashgrid_corners": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                     c_void_p, c_void_p]),
+    "dvt_hashgrid_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p]),
+    "dvt_hashgrid_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p]),
+    "dvt_fit_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "dvt_fit_destroy": (None, [c_void_p]),
+    "dvt_fit_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    "dvt_fit_get_param": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    "dvt_fit_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_float, c_float, c_int, c_float,
+                              c_float, c_float]),
+    "dvt_fit_run": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "dvt_fit_losses": (c_int, [c_void_p, c_void_p, c_int]),
+    "dvt_fit_query": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dvt_fit_residual": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dvt_vit_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float]),
     "dvt_vit_destroy": (None, [c_void_p]),
     "dvt_vit_load": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),

@@ -83,3 +83,40 @@ def im2col(x: torch.Tensor, patch: int, stride: int) -> torch.Tensor:
     out = torch.empty((B * h * w, kp), device=x.device, dtype=torch.bfloat16)
     check(lib().dvt_im2col(ptr(x), _dt(x), ptr(out), B, H, W, patch, stride, cur_stream()), "dvt_im2col")
     return out
+
+
+def gemm_bf16_ex(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+                 out_dtype: torch.dtype = torch.float32, splits: int = 1, last_col: bool = False):
+    """out[M,N] = A . B^T with A given as [M,K] (a_mn False) or [K,M] (a_mn True); B as [N,K] or [K,N]."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    atomic = splits > 1 or last_col
+    n_out = N - 1 if last_col else N
+    ldo = (n_out + 3) // 4 * 4
+    out = (torch.zeros if atomic else torch.empty)((M, ldo), device=a.device, dtype=out_dtype)
+    lc = torch.zeros(M, device=a.device, dtype=torch.float32) if last_col else None
+    check(lib().dvt_gemm_bf16_ex(ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), M, N, K, ptr(out),
+                                 out.stride(0), _dt(out), splits, ptr(lc), cur_stream()), "dvt_gemm_bf16_ex")
+    return (out[:, :n_out], lc) if last_col else out[:, :n_out]
+
+
+def split_tf32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [..] -> [2, ..]: plane 0 = TF32-exact part (low 13 mantissa bits cleared), plane 1 = remainder."""
+    hi = (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    return torch.stack([hi, x - hi]).contiguous()
+
+
+def gemm_f32x3(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+               splits: int = 1, last_col: bool = False):
+    """fp32-accurate product of fp32 matrices on the tensor cores (3xTF32).  a / b are plain fp32 matrices
+    ([M,K] or [K,M] when a_mn; [N,K] or [K,N] when b_mn); they are split into hi/lo planes here."""
+    _need_cuda(a, b)
+    ap, bp = split_tf32(a), split_tf32(b)
+    atomic = splits > 1 or last_col
+    n_out = N - 1 if last_col else N
+    ldo = (n_out + 3) // 4 * 4
+    out = (torch.zeros if atomic else torch.empty)((M, ldo), device=a.device, dtype=torch.float32)
+    lc = torch.zeros(M, device=a.device, dtype=torch.float32) if last_col else None
+    check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], a.numel(), int(a_mn), ptr(bp), b.shape[1], b.numel(), int(b_mn), M, N,
+                               K, ptr(out), out.stride(0), splits, ptr(lc), cur_stream()), "dvt_gemm_f32x3")
+    return (out[:, :n_out], lc) if last_col else out[:, :n_out]

@@ -1,0 +1,90 @@
+"""Stage-1 of DVT on one GPU: feature-bank extraction (HP-1) + per-image neural-field fit (HP-2).
+
+This is the public call the stage-1 CLI (`main_img_denoising.py`) and `bench.py` make per image; it replaces the
+body of the reference's per-image loop (main_img_denoising.py:301-343): 769 ViT forwards into a device-resident
+bank, then `denoise_an_image`.  Everything that computes runs in libdvt_b200.so."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import models as DVT
+from .fit import FitEngine, make_patch_coordinates
+
+
+@dataclass
+class Stage1Config:
+    num_iters: int = 25000
+    warmup_iters: int = 2500
+    n_levels: int = 16
+    freeze_shared_artifacts_after: float = 0.5
+    lr: float = 0.01
+    min_lr: float = 0.001
+    weight_decay: float = 1e-5
+    extract_bsz: int = 32
+    pixel_bsz: int = 2048
+    loss_scale: float = 1024.0      # torch.amp.GradScaler("cuda", 2**10), never unscaled (main_img_denoising.py:55,88)
+    graph_steps: int = 10
+
+
+class Stage1Pipeline:
+    def __init__(self, vit: DVT.PretrainedViTWrapper, layer_index: int, input_size, cfg: Stage1Config):
+        self.vit, self.layer_index, self.cfg = vit, layer_index, cfg
+        H, W = input_size
+        P, S = vit.patch_size, vit.stride
+        self.h, self.w = (H - P) // S + 1, (W - P) // S + 1
+        self.C = vit.n_output_dims
+        self.input_size = (H, W)
+        self.field = DVT.NeuralFeatureField(feat_dim=self.C, n_levels=cfg.n_levels)
+        self.engine = FitEngine(self.C, self.h, self.w, cfg.pixel_bsz, self.field.meta)
+        self._bank: Optional[torch.Tensor] = None
+        self._stage: Optional[torch.Tensor] = None
+
+    # ---- HP-1 ----------------------------------------------------------------------------------------------
+    def extract_bank(self, views: torch.Tensor) -> torch.Tensor:
+        """views [V, 3, H, W] (cuda, or pinned host memory: copied batch by batch) -> bank [V, h, w, C] fp32 (cuda)."""
+        V = views.shape[0]
+        if self._bank is None or self._bank.shape[0] != V:
+            self._bank = torch.empty((V, self.h, self.w, self.C), device="cuda", dtype=torch.float32)
+        bsz = self.cfg.extract_bsz
+        for s in range(0, V, bsz):
+            x = views[s:s + bsz]
+            if not x.is_cuda:
+                if self._stage is None or self._stage.shape[0] < x.shape[0] or self._stage.dtype != x.dtype:
+                    self._stage = torch.empty((bsz,) + tuple(views.shape[1:]), device="cuda", dtype=x.dtype)
+                dst = self._stage[:x.shape[0]]
+                dst.copy_(x, non_blocking=True)
+                x = dst
+            feats = self.vit.get_intermediate_layers(x, n=[self.layer_index], reshape=True)[-1]  # NCHW view of NHWC
+            self._bank[s:s + x.shape[0]] = feats.permute(0, 2, 3, 1)
+        return self._bank
+
+    # ---- HP-2 ----------------------------------------------------------------------------------------------
+    def denoise(self, bank: torch.Tensor, coords: torch.Tensor, idx_stream: np.ndarray,
+                init: Optional[Dict[str, torch.Tensor]] = None, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """bank [V, h, w, C] f32 cuda, coords [V, h, w, 2] in [0,1]; the last view is the un-augmented image.
+        Returns denoised_feats [1, h, w, C] (= neural_field(coords[-1]), what the reference saves) and raw [h, w, C]."""
+        cfg = self.cfg
+        den = DVT.SingleImageDenoiser(self.h, self.w, self.C, layer_index=self.layer_index)
+        if seed is not None:
+            g = torch.Generator().manual_seed(seed)
+            with torch.no_grad():
+                self.field.neural_field.params.copy_((torch.rand(self.field.meta.n_params, generator=g) * 2 - 1) * 1e-4)
+        if init is not None:
+            self.engine.load_modules(den, self.field)
+            for k, v in init.items():
+                self.engine.set_param(k, v)
+        else:
+            self.engine.load_modules(den, self.field)
+        V = bank.shape[0]
+        self.engine.begin(bank.reshape(V * self.h * self.w, self.C), coords.reshape(-1, 2).to("cuda", torch.float32).contiguous(),
+                          idx_stream, lr=cfg.lr, min_lr=cfg.min_lr, warmup_iters=cfg.warmup_iters,
+                          freeze_after=cfg.freeze_shared_artifacts_after, weight_decay=cfg.weight_decay,
+                          loss_scale=cfg.loss_scale)
+        self.engine.run(graph_steps=cfg.graph_steps)
+        full = make_patch_coordinates(self.h, self.w, 0, 1).to("cuda")
+        denoised = self.engine.query(full).reshape(1, self.h, self.w, self.C)
+        return {"denoised_feats": denoised, "raw": bank[-1], "denoiser": den}

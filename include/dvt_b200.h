@@ -40,6 +40,8 @@ int dvt_version(void);
 const char* dvt_last_error(void);
 /* Reads (and clears) the device-side error word written by a kernel watchdog; 0 = none. */
 int dvt_device_error(unsigned int* code_out);
+/* Number of kernels this library has launched in the calling process (CUDA-graph replays count their nodes). */
+long long dvt_launch_count(void);
 /* Process-wide kernel implementation switch for debugging: 0 = tcgen05 tensor-core kernels (default),
  * 1 = plain SIMT reference kernels (same semantics, slow).  Also settable with DVT_GEMM_IMPL=simt. */
 int dvt_set_debug_impl(int impl);
@@ -103,6 +105,71 @@ int dvt_vit_reserve(dvt_vit_t* h, int max_batch, int H, int W, int stride);
 int dvt_vit_forward(dvt_vit_t* h, const void* x, int x_dtype, int B, int H, int W, int stride,
                     const float* pos_patch, const float* prefix_rows, int layer_index, int norm, float* out,
                     int all_tokens, void* stream);
+
+/* General form of dvt_gemm_tn for bf16 operands: a_mn / b_mn = 1 reads the operand from its transposed storage
+ * ([K, M] / [K, N] row-major, "MN-major") without a copy -- how the fit's weight-gradient GEMMs read activations.
+ * Supported: (a_mn, b_mn) in {(0,0), (0,1), (1,1)}.  last_col_out (optional, splits >= 1, fp32 out): column N-1 of
+ * the product is accumulated into last_col_out[M] instead of out (bias gradient via a ones column in B). */
+int dvt_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
+                     void* out, int ldo, int out_dtype, int splits, float* last_col_out, void* stream);
+
+/* fp32-accurate GEMM on the tensor cores ("3xTF32"): every fp32 operand is given as two planes, hi = the TF32-exact
+ * part (low 13 mantissa bits zero) at the pointer and lo = x - hi at pointer + plane (elements); the kernel
+ * accumulates A_hi.B_hi + A_hi.B_lo + A_lo.B_hi in fp32.  a_mn / b_mn as in dvt_gemm_bf16_ex.  This is what the
+ * stage-1 fit uses for nn.Linear forward/backward (the reference runs them in fp32 on cuBLAS:
+ * dvt/models/neural_feature_field.py:40-44, dvt/models/offline_denoiser.py:40-46 with --dtype float32). */
+int dvt_gemm_f32x3(const float* A, int lda, size_t plane_a, int a_mn, const float* B, int ldb, size_t plane_b, int b_mn,
+                   int M, int N, int K, float* out, int ldo, int splits, float* last_col_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * multiresolution hash grid, 2-D inputs, 8 features per level (replaces tcnn.Encoding(HashGrid) created at
+ * dvt/models/neural_feature_field.py:25-39).  The level table (scale, resolution, entries, offsets, hashed flag per
+ * level) is computed by the caller exactly as tiny-cuda-nn does (dvt/models/hashgrid_meta.py) and passed in:
+ * HOST arrays scale[L] (f32), res[L], size[L], offset[L+1], hashed[L] (u32).
+ * ------------------------------------------------------------------------------------------------------- */
+/* idx [n, L, 4] u32 (entry index incl. level offset) and w [n, L, 4] f32 of the 4 interpolation corners. */
+int dvt_hashgrid_corners(int n_levels, const float* scale_host, const uint32_t* res_host, const uint32_t* size_host,
+                         const uint32_t* offset_host, const uint32_t* hashed_host, const float* coords, int n,
+                         uint32_t* idx_out, float* w_out, void* stream);
+/* out [n, L*8] f32 = encoding of coords [n, 2] with table [entries, 8] f32. */
+int dvt_hashgrid_fwd(int n_levels, const float* scale_host, const uint32_t* res_host, const uint32_t* size_host,
+                     const uint32_t* offset_host, const uint32_t* hashed_host, const float* table, const float* coords,
+                     int n, float* out, void* stream);
+/* grad_table [entries, 8] f32 += d out / d table contracted with dout [n, L*8] (dense gradient, like tcnn). */
+int dvt_hashgrid_bwd(int n_levels, const float* scale_host, const uint32_t* res_host, const uint32_t* size_host,
+                     const uint32_t* offset_host, const uint32_t* hashed_host, const float* coords, int n,
+                     const float* dout, float* grad_table, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * HP-2: per-image neural-field fit (replaces the loop of denoise_an_image, main_img_denoising.py:39-89, i.e.
+ * SingleImageDenoiser.forward + NeuralFeatureField.forward + torch.optim.Adam.step per iteration)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct dvt_fit dvt_fit_t;
+
+/* feat_dim C (multiple of 32), noise map gh x gw, pixel batch `bsz` (args.pixel_bsz), hash-grid level table. */
+int dvt_fit_create(dvt_fit_t** out, int feat_dim, int gh, int gw, int bsz, int n_levels, const float* scale_host,
+                   const uint32_t* res_host, const uint32_t* size_host, const uint32_t* offset_host,
+                   const uint32_t* hashed_host);
+void dvt_fit_destroy(dvt_fit_t* h);
+/* Parameters by name, fp32, host or device: "G" (shared_artifacts [1,C,gh,gw]), "res.{0,2,4}.{weight,bias}"
+ * (residual_predictor), "table" (tcnn params, [entries*8]), "mlp.{0,2}.{weight,bias}" (NeuralFeatureField.mlp). */
+int dvt_fit_set_param(dvt_fit_t* h, const char* name, const float* src, size_t numel);
+int dvt_fit_get_param(dvt_fit_t* h, const char* name, float* dst, size_t numel);
+/* Starts a fit: zeroes Adam state, installs the bank (device, borrowed: feats f32 [rows, C], coords f32 [rows, 2],
+ * rows = views*gh*gw, row r belongs to noise-map cell r % (gh*gw)), the sampling stream idx_host int32
+ * [num_iters, bsz] (np.random.randint replay) and the schedule (adjust_learning_rate, dvt/utils/misc.py:306-322;
+ * freeze step = int(freeze_after * num_iters)). */
+int dvt_fit_begin(dvt_fit_t* h, const float* bank_feats, const float* bank_coords, size_t bank_rows,
+                  const int32_t* idx_host, int num_iters, float lr, float min_lr, int warmup_iters, float freeze_after,
+                  float weight_decay, float loss_scale);
+/* Runs the next `count` optimisation steps.  graph_steps > 0: CUDA graphs of that many steps. */
+int dvt_fit_run(dvt_fit_t* h, int count, int graph_steps, void* stream);
+/* Per-step losses, HOST f32 [num_iters, 5]: loss, patch_l2, cosine_similarity, residual, residual_sparsity. */
+int dvt_fit_losses(dvt_fit_t* h, float* dst_host, int num_iters);
+/* out [n, C] f32 = neural_field(coords [n, 2])  (denoised_feats of the final query, main_img_denoising.py:121-130). */
+int dvt_fit_query(dvt_fit_t* h, const float* coords, int n, float* out, void* stream);
+/* out [n, C] f32 = residual_predictor(raw [n, C] f32). */
+int dvt_fit_residual(dvt_fit_t* h, const float* raw, int n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

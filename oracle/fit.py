@@ -155,7 +155,7 @@ def fit(bank_feats: torch.Tensor, bank_coords: torch.Tensor, h: int, w: int, met
         (out["loss"] * loss_scale).backward()
         opt.step()
         if step % log_every == 0 or step == num_iters - 1:
-            logs.append([step] + [float(out.get(k, torch.zeros(()))) for k in
+            logs.append([step] + [float(out[k].detach()) if k in out else 0.0 for k in
                                   ("loss", "patch_l2_loss", "cosine_similarity_loss", "residual_loss",
                                    "residual_sparsity_loss")])
     final = {k: v.detach() for k, v in p.items()}

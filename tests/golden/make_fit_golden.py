@@ -101,7 +101,7 @@ def reference_run(cfg, feats, coords, meta, init, idx_stream):
         (loss * cfg["loss_scale"]).backward()   # grad_scaler.scale(loss).backward(); never unscaled (:88-89)
         optimizer.step()
         if step % cfg["log_every"] == 0 or step == args.num_iters - 1:
-            logs.append([step] + [float(out.get(k, torch.zeros(()))) for k in
+            logs.append([step] + [float(out[k].detach()) if k in out else 0.0 for k in
                                   ("loss", "patch_l2_loss", "cosine_similarity_loss", "residual_loss",
                                    "residual_sparsity_loss")])
     with torch.no_grad():

@@ -1,0 +1,103 @@
+"""Pins oracle/fit.py + oracle/hashgrid.py against the golden fixtures produced with the reference's own
+SingleImageDenoiser / adjust_learning_rate (tests/golden/make_fit_golden.py), and checks the host-side pieces the
+CUDA path shares with it (level table, schedule, coordinate conventions)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fit as OF
+from oracle import hashgrid as HG
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden(name):
+    z = np.load(os.path.join(GOLD, f"fit_{name}.npz"))
+    cfg = {k: v for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    for k in ("C", "h", "w", "V", "bsz", "n_levels", "num_iters", "warmup_iters", "log_every", "seed"):
+        cfg[k] = int(cfg[k])
+    return cfg, z
+
+
+@pytest.mark.parametrize("name", ["small_L6_ls1", "hashed_L16"])
+def test_oracle_reproduces_reference_golden(name):
+    cfg, z = _golden(name)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    meta = HG.grid_meta(cfg["n_levels"])
+    feats, coords = OF.synthetic_bank(cfg["V"], cfg["h"], cfg["w"], cfg["C"], seed=cfg["seed"])
+    init = OF.init_params(cfg["C"], cfg["h"], cfg["w"], meta, seed=cfg["seed"])
+    idx = np.random.RandomState(cfg["seed"]).randint(0, cfg["V"] * cfg["h"] * cfg["w"], (cfg["num_iters"], cfg["bsz"]))
+    assert int(idx.sum()) == int(z["idx_checksum"][0])
+    out = OF.fit(feats, coords, cfg["h"], cfg["w"], meta, init, idx, lr=cfg["lr"], min_lr=cfg["min_lr"],
+                 weight_decay=cfg["weight_decay"], warmup_iters=cfg["warmup_iters"], freeze_after=cfg["freeze_after"],
+                 loss_scale=cfg["loss_scale"], log_every=cfg["log_every"])
+    assert np.allclose(out["logs"], z["logs"], rtol=2e-3, atol=1e-5)
+    d = (out["denoised_feats"] - torch.from_numpy(z["denoised_feats"])).abs().max().item()
+    assert d < 2e-3, d
+    assert (out["params"]["G"] - torch.from_numpy(z["G_final"])).abs().max().item() < 1e-3
+
+
+def test_level_table_matches_survey():
+    m = HG.grid_meta(16)
+    assert list(map(int, m.res)) == [16, 22, 28, 37, 49, 65, 85, 112, 148, 195, 257, 338, 446, 589, 777, 1025]
+    assert m.n_entries == 2467720 and m.n_params == 19741760
+    assert list(m.hashed) == [False] * 15 + [True]
+    m10 = HG.grid_meta(10)
+    assert list(map(int, m10.res)) == [16, 26, 41, 64, 102, 162, 256, 407, 646, 1024]
+    assert not m10.hashed.any() and m10.n_params == 13923712
+
+
+def test_product_level_table_equals_oracle():
+    from dvt.models.hashgrid_meta import make_meta
+    for L in (1, 2, 6, 10, 16):
+        a, b = make_meta(L), HG.grid_meta(L)
+        assert np.array_equal(a.scale, b.scale) and np.array_equal(a.res, b.res) and np.array_equal(a.size, b.size)
+        assert np.array_equal(a.offset, b.offset) and np.array_equal(a.hashed.astype(bool), b.hashed)
+
+
+def test_hashgrid_properties():
+    meta = HG.grid_meta(16)
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(meta.n_entries, 8, generator=g)
+    c = torch.rand(512, 2, generator=g)
+    # interpolation weights are a partition of unity and indices stay inside their level
+    for l in range(16):
+        idx, w = HG.corner_indices_weights(c, meta, l)
+        assert torch.allclose(w.sum(1), torch.ones(512), atol=1e-6)
+        assert int(idx.min()) >= 0 and int(idx.max()) < int(meta.size[l])
+    # linearity in the table
+    e1 = HG.encode(table, c, meta)
+    e2 = HG.encode(2.5 * table, c, meta)
+    assert torch.allclose(e2, 2.5 * e1, rtol=1e-5, atol=1e-6)
+    # a constant table encodes to that constant (weights sum to one)
+    e3 = HG.encode(torch.full((meta.n_entries, 8), 0.75), c, meta)
+    assert torch.allclose(e3, torch.full_like(e3, 0.75), atol=1e-5)
+
+
+def test_lr_schedule_and_coordinates():
+    # dvt/utils/misc.py:306-322
+    assert OF.lr_at(0, 0.01, 0.001, 200, 2000) == 0.0
+    assert math.isclose(OF.lr_at(100, 0.01, 0.001, 200, 2000), 0.005)
+    assert math.isclose(OF.lr_at(200, 0.01, 0.001, 200, 2000), 0.01)
+    assert math.isclose(OF.lr_at(2000, 0.01, 0.001, 200, 2000), 0.001)
+    c = OF.make_patch_coordinates(3, 5)
+    assert c.shape == (3, 5, 2) and float(c[0, 0, 0]) == -1 and float(c[0, 4, 0]) == 1 and float(c[2, 0, 1]) == 1
+    from dvt.fit import make_patch_coordinates
+    assert torch.equal(make_patch_coordinates(37, 37, 0, 1), OF.make_patch_coordinates(37, 37, 0, 1))
+
+
+def test_patch_cell_indexing_is_exact():
+    """Row r of the flattened bank belongs to noise-map cell r % (h*w): the reference's tiled linspace(-1,1)
+    G-coordinates (main_img_denoising.py:58-62) sample exactly that node of G (bit-exact patch indexing)."""
+    h, w, V, C = 5, 7, 3, 4
+    G = torch.randn(1, C, h, w, generator=torch.Generator().manual_seed(0))
+    gc = OF.make_patch_coordinates(h, w).unsqueeze(0).repeat(V, 1, 1, 1).reshape(-1, 2)
+    rows = torch.arange(V * h * w)
+    s = torch.nn.functional.grid_sample(G, gc[None, None, ...], mode="bilinear", align_corners=True)
+    s = s.squeeze().permute(1, 0)
+    cell = rows % (h * w)
+    direct = G[0].permute(1, 2, 0).reshape(h * w, C)[cell]
+    assert torch.allclose(s, direct, atol=1e-5)
