@@ -92,11 +92,24 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port, fp32 PyTorch CPU) on a bounded sample, extrapolated per image
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(args, views_sample: int = 2, fit_steps: int = 4):
+def usable_cpus() -> int:
+    """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota (a container that sees 128
+    logical CPUs but is limited to a few cores thrashes when given 128 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def cpu_reference_rate(args, views_sample: int = 1, fit_steps: int = 2):
     from oracle import fit as OF
     from oracle import hashgrid as HG
     from oracle import vit as OV
-    cores = os.cpu_count() or 1
+    cores = min(usable_cpus(), 32)  # measured on the GPU box: 128 threads run these ops ~100x slower than 8-32 do
     torch.set_num_threads(cores)
     cfg = OV.CONFIGS[MODEL]
     sd = OV.random_state_dict(cfg, seed=0)
@@ -148,7 +161,7 @@ def run_reference_arm(args, rank):
     vals, last = [], None
     for _ in range(max(1, args.warmup > 0) + args.steps):
         t0 = time.perf_counter()
-        last = cpu_reference_rate(args, views_sample=1, fit_steps=2)
+        last = cpu_reference_rate(args, views_sample=1, fit_steps=1)
         vals.append((last["value"], time.perf_counter() - t0))
     vals = vals[1:] if len(vals) > 1 else vals
     v = float(np.mean([a for a, _ in vals]))

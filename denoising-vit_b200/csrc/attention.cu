@@ -4,9 +4,9 @@
 //   out  : bf16 [B, N, C]    (col = h*64 + d; directly the A operand of the out-projection GEMM)
 //
 // One CTA per (query tile of 128 rows, head, image), 6 warps:
-//   warp 0     TMA producer: Q tile once, then K/V tiles (128 keys x 64) through a 2-deep ring (3-D tensor map
+//   warp 0     TMA producer: Q tile once, then K (1 slot) / V (2 slots) tiles of 128 keys x 64 (3-D tensor map
 //              over [3C, N, B]; keys past N are zero-filled)
-//   warp 1     MMA issuer: S = Q.K^T (M128 N128 K16 x4, K-major operands) into one of two TMEM buffers;
+//   warp 1     MMA issuer: S = Q.K^T (M128 N128 K16 x4, K-major operands) into TMEM;
 //              O_j = P_j.V_j (M128 N64 K16 x8; P from smem K-major, V straight from its TMA tile as an MN-major
 //              operand) into one of two TMEM buffers
 //   warps 2-5  softmax: one thread per query row (TMEM lane = row): tcgen05.ld S, online max / exp2 / sum in
@@ -25,17 +25,19 @@ constexpr int ATT_BK = 128;
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 // smem layout (offsets from a 1024-aligned base)
+// Sized so that TWO CTAs are resident per SM (96 KB smem, 256 TMEM columns each): the softmax of one CTA overlaps
+// the tensor-core work of the other, which hides most of the exp/max latency a single softmax warpgroup exposes.
 constexpr int ATT_OFF_Q = 0;
-constexpr int ATT_OFF_K = ATT_OFF_Q + ATT_TILE_BYTES;          // 2 stages
-constexpr int ATT_OFF_V = ATT_OFF_K + 2 * ATT_TILE_BYTES;      // 2 stages
-constexpr int ATT_OFF_P = ATT_OFF_V + 2 * ATT_TILE_BYTES;      // 2 buffers x 2 k-atoms x 16 KB
-constexpr int ATT_OFF_BAR = ATT_OFF_P + 4 * ATT_TILE_BYTES;
-constexpr int ATT_NUM_BARS = 1 + 2 + 2 + 2 + 2 + 2 + 2 + 2 + 2;
+constexpr int ATT_OFF_K = ATT_OFF_Q + ATT_TILE_BYTES;          // 1 stage (freed as soon as QK_j completes)
+constexpr int ATT_OFF_V = ATT_OFF_K + ATT_TILE_BYTES;          // 2 stages
+constexpr int ATT_OFF_P = ATT_OFF_V + 2 * ATT_TILE_BYTES;      // 1 buffer x 2 k-atoms x 16 KB
+constexpr int ATT_OFF_BAR = ATT_OFF_P + 2 * ATT_TILE_BYTES;
+constexpr int ATT_NUM_BARS = 1 + 1 + 1 + 2 + 2 + 1 + 1 + 1 + 2;
 constexpr int ATT_OFF_TMEM = ATT_OFF_BAR + ATT_NUM_BARS * 8;
 constexpr int ATT_SMEM_TOTAL = ATT_OFF_TMEM + 16 + 1024;
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
-constexpr uint32_t ATT_TMEM_COLS = 512;
-constexpr uint32_t ATT_TM_S = 0, ATT_TM_O = 256;
+// TMEM columns: S [0,128) O0 [128,192) O1 [192,256)
+constexpr uint32_t ATT_TMEM_COLS = 256;
+constexpr uint32_t ATT_TM_S = 0, ATT_TM_O = 128;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -43,7 +45,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int C,
                     float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
@@ -55,13 +57,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 3;
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 7;
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_empty = bars + 11;
-  uint64_t* p_full = bars + 13;
-  uint64_t* o_full = bars + 15;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;   // [2]
+  uint64_t* v_empty = bars + 5;  // [2]
+  uint64_t* s_full = bars + 7;
+  uint64_t* s_empty = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* o_full = bars + 10;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ATT_OFF_TMEM);
 
   const int warp = threadIdx.x >> 5;
@@ -74,14 +76,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
       mbar_init(&o_full[i], 1);
     }
     fence_mbar_init();
@@ -103,9 +105,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1, 10);
-        mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
-        tma_load_3d(sK + st * ATT_TILE_BYTES, &tm_qkv, &k_full[st], C + head * ATT_D, j * ATT_BK, b);
+        mbar_wait(k_empty, (j & 1) ^ 1, 10);
+        mbar_expect_tx(k_full, ATT_TILE_BYTES);
+        tma_load_3d(sK, &tm_qkv, k_full, C + head * ATT_D, j * ATT_BK, b);
         mbar_wait(&v_empty[st], ph ^ 1, 11);
         mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
         tma_load_3d(sV + st * ATT_TILE_BYTES, &tm_qkv, &v_full[st], 2 * C + head * ATT_D, j * ATT_BK, b);
@@ -117,18 +119,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       constexpr uint32_t idesc_s = make_idesc(1, 128, 128, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc(1, 128, 64, 0, 1);   // P (K-major) x V (MN-major)
       auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_full[st], ph, 12);
-        mbar_wait(&s_empty[st], ph ^ 1, 13);
+        const uint32_t ph = j & 1;
+        mbar_wait(k_full, ph, 12);
+        mbar_wait(s_empty, ph ^ 1, 13);
         tc_fence_after();
         const uint64_t da = make_smem_desc(smem_u32(sQ), 0, 1024, 2);
-        const uint64_t db = make_smem_desc(smem_u32(sK + st * ATT_TILE_BYTES), 0, 1024, 2);
+        const uint64_t db = make_smem_desc(smem_u32(sK), 0, 1024, 2);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + ATT_TM_S + st * 128, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k > 0);
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[st]);
+          umma_f16(tmem_base + ATT_TM_S, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(k_empty);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0, 14);
       issue_qk(0);
@@ -137,10 +138,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&v_full[st], ph, 15);
-        mbar_wait(&p_full[st], ph, 16);
+        mbar_wait(p_full, j & 1, 16);
         tc_fence_after();
-        // P buffer st: two K-atoms (keys 0-63, 64-127), each a [128 x 128B] swizzled tile
-        const uint32_t p_base = smem_u32(sP + st * 2 * ATT_TILE_BYTES);
+        // P buffer: two K-atoms (keys 0-63, 64-127), each a [128 x 128B] swizzled tile
+        const uint32_t p_base = smem_u32(sP);
         const uint32_t v_base = smem_u32(sV + st * ATT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -165,9 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     float l_run = 0.f;
 
     for (int j = 0; j < T; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&s_full[st], ph, 17);
+      mbar_wait(s_full, j & 1, 17);
       tc_fence_after();
       // ---- pass 1: row max over this tile (TMEM is re-read in pass 2: cheaper than 128 live registers) ----
       const int kbase = j * ATT_BK;
@@ -176,7 +175,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t sreg[32];
-        tmem_ld_32x32(lane_addr + ATT_TM_S + st * 128 + c * 32, sreg);
+        tmem_ld_32x32(lane_addr + ATT_TM_S + c * 32, sreg);
         tmem_ld_wait();
         if (partial) {
 #pragma unroll
@@ -190,17 +189,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       m_tile *= scale_log2e;                      // scale > 0: max commutes with the scaling
       const float m_new = fmaxf(m_run, m_tile);  // finite: every tile has at least one valid key
       const float alpha = ex2(m_run - m_new);     // 0 on the first tile (m_run = -inf)
+      // ---- fold in the previous tile's O (also proves PV_{j-1} has finished reading the single P buffer) ----
+      if (j > 0) {
+        const int pst = (j - 1) & 1;
+        const uint32_t pph = ((j - 1) >> 1) & 1;
+        mbar_wait(&o_full[pst], pph, 18);
+        tc_fence_after();
+        uint32_t o[2][32];
+        tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64, o[0]);
+        tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64 + 32, o[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < ATT_D; ++d) acc[d] = (acc[d] + __uint_as_float(o[d >> 5][d & 31])) * alpha;
+      }
       // ---- pass 2: p = exp2(s*scale - m_new), row sum, bf16 pack, swizzled store ----
       float l_tile = 0.f;
-      uint8_t* pbuf = sP + st * 2 * ATT_TILE_BYTES;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t sreg[32];
-        tmem_ld_32x32(lane_addr + ATT_TM_S + st * 128 + c * 32, sreg);
+        tmem_ld_32x32(lane_addr + ATT_TM_S + c * 32, sreg);
         tmem_ld_wait();
         if (c == 3) {
           tc_fence_before();
-          mbar_arrive(&s_empty[st]);  // S buffer may now be overwritten by QK of tile j+2
+          mbar_arrive(s_empty);  // S may now be overwritten by QK of tile j+1
         }
         uint32_t packed[16];
 #pragma unroll
@@ -215,7 +226,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           packed[i] = pack_bf16x2(p0, p1);
         }
         // keys [c*32, c*32+32) -> k-atom (c >> 1), 16B chunks ((c & 1) * 4 + q), q = 0..3
-        uint8_t* atom = pbuf + (c >> 1) * ATT_TILE_BYTES + row * 128;
+        uint8_t* atom = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
@@ -224,21 +235,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         }
       }
       fence_async_smem();  // generic-proxy writes of P -> visible to tcgen05.mma
-      mbar_arrive(&p_full[st]);
-      // ---- fold in the previous tile's O, rescale to the new max ----
-      if (j > 0) {
-        const int pst = (j - 1) & 1;
-        const uint32_t pph = ((j - 1) >> 1) & 1;
-        mbar_wait(&o_full[pst], pph, 18);
-        tc_fence_after();
-        uint32_t o[2][32];
-        tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64, o[0]);
-        tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64 + 32, o[1]);
-        tmem_ld_wait();
-        tc_fence_before();
-#pragma unroll
-        for (int d = 0; d < ATT_D; ++d) acc[d] = (acc[d] + __uint_as_float(o[d >> 5][d & 31])) * alpha;
-      }
+      tc_fence_before();
+      mbar_arrive(p_full);
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
     }

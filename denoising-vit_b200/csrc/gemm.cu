@@ -230,7 +230,6 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool has_k = kb0 < kb_total;
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
-      const int m_thread = tm * BM + quad * 32 + lane;  // row owned in the TMEM layout
       const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -243,47 +242,74 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         const int n_base = tn * BN + c * 32;
         if (n_base >= s.N) continue;  // whole chunk out of range (warp-uniform)
-        // ---- pre-stage: thread-per-row ----
-        float v[32];
-        const bool row_ok = m_thread < s.M;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float acc = has_k ? __uint_as_float(r[j]) : 0.0f;
-          int n = n_base + j;
-          v[j] = (row_ok && n < s.N) ? epi_pre(e, m_thread, n, acc) : 0.0f;
-        }
-        if (e.out_t) {
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              int n = n_base + j;
-              if (n < s.N) e.out_t[(size_t)n * e.ldt + m_thread] = __float2bfloat16_rn(v[j]);
-            }
-          }
-        }
-        if (e.out == nullptr) continue;
-        // ---- transpose through smem: afterwards each lane holds 4 consecutive columns of 8 rows ----
+        // ---- transpose through smem: afterwards each lane holds 4 consecutive columns of 8 rows.  No math on the
+        // thread-per-row registers: everything that depends on the column (bias, LayerScale, ...) is loaded once per
+        // chunk as a float4 in the coalesced layout below.
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(scr + lane * SCR_PITCH + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          *reinterpret_cast<uint4*>(scr + lane * SCR_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
         const int col4 = (lane & 7) * 4;
         const int n = n_base + col4;
-        const bool vec_ok = (n + 3 < s.N);
+        const int m0 = tm * BM + quad * 32 + (lane >> 3);
+        if (n + 3 < s.N) {
+          // ---------------- vector path ----------------
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (e.out_mode == OUT_F32_RESID && e.gamma) g4 = __ldg(reinterpret_cast<const float4*>(e.gamma + n));
+          float4 xin[8];
+          if (e.out_mode == OUT_F32_RESID) {  // issue all residual loads before any store (memory-level parallelism)
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int i = (lane >> 3) + 4 * jj;
-          const int m = tm * BM + quad * 32 + i;
-          float4 x = *reinterpret_cast<const float4*>(scr + i * SCR_PITCH + col4);
-          if (m < s.M) {
-            if (vec_ok) {
-              epi_post4(e, m, n, x);
-            } else {
-              if (n + 0 < s.N) epi_post1(e, m, n + 0, x.x);
-              if (n + 1 < s.N) epi_post1(e, m, n + 1, x.y);
-              if (n + 2 < s.N) epi_post1(e, m, n + 2, x.z);
-              if (n + 3 < s.N) epi_post1(e, m, n + 3, x.w);
+            for (int jj = 0; jj < 8; ++jj) {
+              const int m = m0 + 4 * jj;
+              if (m < s.M) xin[jj] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) + (size_t)m * e.ldo + n);
             }
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int i = (lane >> 3) + 4 * jj;
+            const int m = m0 + 4 * jj;
+            float4 x = *reinterpret_cast<const float4*>(scr + i * SCR_PITCH + col4);
+            if (m >= s.M) continue;
+            if (!has_k) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+            if (e.act == ACT_GELU) {
+              x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+            } else if (e.act == ACT_RELU) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            }
+            if (e.mask_f32) {
+              const float4 h = *reinterpret_cast<const float4*>(e.mask_f32 + (size_t)m * e.ldmask + n);
+              x.x = h.x > 0.f ? x.x : 0.f; x.y = h.y > 0.f ? x.y : 0.f; x.z = h.z > 0.f ? x.z : 0.f; x.w = h.w > 0.f ? x.w : 0.f;
+            } else if (e.mask) {
+              const uint2 hb = *reinterpret_cast<const uint2*>(e.mask + (size_t)m * e.ldmask + n);
+              const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
+              const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
+              x.x = __low2float(h01) > 0.f ? x.x : 0.f; x.y = __high2float(h01) > 0.f ? x.y : 0.f;
+              x.z = __low2float(h23) > 0.f ? x.z : 0.f; x.w = __high2float(h23) > 0.f ? x.w : 0.f;
+            }
+            if (e.alpha != 1.0f) { x.x *= e.alpha; x.y *= e.alpha; x.z *= e.alpha; x.w *= e.alpha; }
+            if (e.out_mode == OUT_F32_RESID) {
+              float4 o = xin[jj];
+              o.x = fmaf(g4.x, x.x, o.x); o.y = fmaf(g4.y, x.y, o.y); o.z = fmaf(g4.z, x.z, o.z); o.w = fmaf(g4.w, x.w, o.w);
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n) = o;
+            } else {
+              epi_post4(e, m, n, x);
+            }
+          }
+        } else {
+          // ---------------- ragged N tail: scalar path ----------------
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int i = (lane >> 3) + 4 * jj;
+            const int m = m0 + 4 * jj;
+            const float4 x = *reinterpret_cast<const float4*>(scr + i * SCR_PITCH + col4);
+            if (m >= s.M) continue;
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (n + q < s.N) epi_post1(e, m, n + q, epi_pre(e, m, n + q, has_k ? xs[q] : 0.0f));
           }
         }
         __syncwarp();
@@ -341,9 +367,7 @@ __global__ void gemm_tn_simt_kernel(const T* __restrict__ A, int lda, const T* _
     __syncthreads();
   }
   if (m < s.M && n < s.N) {
-    float v = epi_pre(e, m, n, acc);
-    if (e.out_t) e.out_t[(size_t)n * e.ldt + m] = __float2bfloat16_rn(v);
-    if (e.out) epi_post1(e, m, n, v);
+    epi_post1(e, m, n, epi_pre(e, m, n, acc));
   }
 }
 

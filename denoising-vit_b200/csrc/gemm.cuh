@@ -26,8 +26,6 @@ struct GemmEpi {
   const float* mask_f32 = nullptr;      // same, fp32 mask tensor
   int ldmask = 0;
   float alpha = 1.0f;                 // v *= alpha (after activation / mask)
-  __nv_bfloat16* out_t = nullptr;     // optional transposed bf16 copy: out_t[n, m], leading dim ldt
-  int ldt = 0;
   // post-stage (coalesced)
   int out_mode = OUT_BF16;
   void* out = nullptr;

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Times the HP-2 fit at the headline size (C=768, 37x37, 769 views, 2048 pixels, 16 levels): steps/s in phase 1 and 2,
+with CUDA graphs on/off.  Also the target of ncu launch lists (--iters small)."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "denoising-vit_b200"))
+import dvt.models as DVT  # noqa: E402
+from dvt.fit import FitEngine  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=400)
+    ap.add_argument("--graph-steps", type=int, default=10)
+    ap.add_argument("--views", type=int, default=769)
+    a = ap.parse_args()
+    C, h, w, V, bsz = 768, 37, 37, a.views, 2048
+    field = DVT.NeuralFeatureField(feat_dim=C, n_levels=16)
+    den = DVT.SingleImageDenoiser(h, w, C)
+    eng = FitEngine(C, h, w, bsz, field.meta)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    bank = torch.randn(V * h * w, C, device="cuda", generator=g)
+    coords = torch.rand(V * h * w, 2, device="cuda", generator=g)
+    idx = np.random.RandomState(0).randint(0, V * h * w, (a.iters, bsz))
+    eng.load_modules(den, field)
+    hyper = dict(lr=0.01, min_lr=0.001, warmup_iters=a.iters // 10, freeze_after=0.5, weight_decay=1e-5, loss_scale=1024.0)
+    for gs in (a.graph_steps, 0):
+        eng.begin(bank, coords, idx, **hyper)
+        half = a.iters // 2 + 1
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        eng.run(half, graph_steps=gs)
+        ev[1].record()
+        eng.run(a.iters - half, graph_steps=gs)
+        ev[2].record()
+        torch.cuda.synchronize()
+        p1, p2 = ev[0].elapsed_time(ev[1]) / half, ev[1].elapsed_time(ev[2]) / (a.iters - half)
+        print(f"graph_steps={gs:3d}: phase1 {p1 * 1e3:8.1f} us/step   phase2 {p2 * 1e3:8.1f} us/step")
+
+
+if __name__ == "__main__":
+    main()
