@@ -174,10 +174,17 @@ int dvt_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, i
   return launch_gemm_tn(A, lda, B, ldb, TMAP_BF16, s, e, reinterpret_cast<cudaStream_t>(stream), eff_impl());
 }
 
+static unsigned long long* g_debug_ts = nullptr;
+int dvt_debug_set_timestamp_buffer(unsigned long long* dev_buf16) {
+  g_debug_ts = dev_buf16;
+  return DVT_OK;
+}
+
 int dvt_gemm_f32x3(const float* A, int lda, size_t plane_a, int a_mn, const float* B, int ldb, size_t plane_b, int b_mn,
                    int M, int N, int K, float* out, int ldo, int splits, float* last_col_out, void* stream) {
   DVT_REQUIRE(A && B && out, "dvt_gemm_f32x3: null pointer");
   GemmEpi e;
+  e.debug_ts = g_debug_ts;
   e.out = out;
   e.ldo = ldo;
   if (splits > 1 || last_col_out) {

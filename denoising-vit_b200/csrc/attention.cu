@@ -164,6 +164,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
     float m_run = -INFINITY;  // running max of s * scale_log2e
     float l_run = 0.f;
+    float alpha_prev = 0.f;   // rescale factor of the previous tile (acc is kept relative to the max BEFORE it)
 
     for (int j = 0; j < T; ++j) {
       mbar_wait(s_full, j & 1, 17);
@@ -199,9 +200,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64, o[0]);
         tmem_ld_32x32(lane_addr + ATT_TM_O + pst * 64 + 32, o[1]);
         tmem_ld_wait();
+        // acc (relative to m_{j-2}) * alpha_{j-1} + O_{j-1} (relative to m_{j-1}): one FFMA per element
 #pragma unroll
-        for (int d = 0; d < ATT_D; ++d) acc[d] = (acc[d] + __uint_as_float(o[d >> 5][d & 31])) * alpha;
+        for (int d = 0; d < ATT_D; ++d) acc[d] = fmaf(acc[d], alpha_prev, __uint_as_float(o[d >> 5][d & 31]));
       }
+      alpha_prev = alpha;
       // ---- pass 2: p = exp2(s*scale - m_new), row sum, bf16 pack, swizzled store ----
       float l_tile = 0.f;
 #pragma unroll
@@ -261,8 +264,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int d = d8 * 8 + 2 * i;
-            const float a0 = (acc[d] + __uint_as_float(o[d >> 5][d & 31])) * inv;
-            const float a1 = (acc[d + 1] + __uint_as_float(o[(d + 1) >> 5][(d + 1) & 31])) * inv;
+            const float a0 = fmaf(acc[d], alpha_prev, __uint_as_float(o[d >> 5][d & 31])) * inv;
+            const float a1 = fmaf(acc[d + 1], alpha_prev, __uint_as_float(o[(d + 1) >> 5][(d + 1) & 31])) * inv;
             w[i] = pack_bf16x2(a0, a1);
           }
           *reinterpret_cast<uint4*>(dst + d8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);

@@ -84,9 +84,40 @@ struct StepRows {
 
 // ----------------------------------------------------------------------------------------------------
 // encode: one thread per (sample, level).
+//
+// "Peek" mode (software-pipelined Adam): the dense Adam sweep of step t runs CONCURRENTLY with the forward /
+// backward of step t+1, so when step t+1 is encoded the table still holds the state of step t.  The encode kernel
+// therefore applies Adam step t on the fly to the (few) entries it reads -- same adam1() arithmetic, same inputs, so
+// the value is bit-identical to what the sweep stores later -- without writing anything back.
 // ----------------------------------------------------------------------------------------------------
+struct AdamScalars {
+  float step_size, inv_bc2_sqrt;  // lr / (1 - b1^t),  1 / sqrt(1 - b2^t)
+};
+
+// Branch-free: one MUFU.SQRT and one MUFU.RCP per parameter (the IEEE sqrtf / division expand to ~40 instructions
+// with slow-path branches, which made the sweep issue-bound instead of HBM-bound).
+__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float wd, float ss, float inv_bc2s) {
+  g = fmaf(wd, p, g);
+  m = fmaf(g - m, 0.1f, m);                 // lerp(m, g, 1 - beta1), beta1 = 0.9
+  v = fmaf(v, 0.99f, 0.01f * g * g);        // beta2 = 0.99
+  float sq;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+  const float denom = fmaf(sq, inv_bc2s, 1e-15f);
+  p = fmaf(-ss, __fdividef(m, denom), p);
+}
+
+struct PeekArgs {       // all null / 0 when the table is up to date
+  const float* m;       // Adam moments of the table
+  const float* v;
+  const float* g[2];    // gradient buffers by step parity
+  const uint32_t* stamp[2];
+  const AdamScalars* sc;
+  float wd;
+  int enabled;
+};
+
 __global__ void fit_encode_kernel(GridLevels g, const float* __restrict__ table, const float* __restrict__ coords,
-                                  StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane) {
+                                  StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane, PeekArgs pk) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * g.n_levels) return;
   const int i = t % n, l = t / n;
@@ -94,13 +125,41 @@ __global__ void fit_encode_kernel(GridLevels g, const float* __restrict__ table,
   const int r = rows ? rows[i] : i;
   const float2 xy = *reinterpret_cast<const float2*>(coords + 2 * (size_t)r);
   const CornerSet c = grid_corners(g, l, xy.x, xy.y);
+  // pending Adam step = (step being encoded) - 1
+  int pstep = 0, par = 0;
+  AdamScalars ps{0.f, 1.f};
+  if (pk.enabled) {
+    pstep = sr.step() - 1;
+    par = pstep & 1;
+    ps = pk.sc[pstep];
+  }
   float acc[FIT_F];
 #pragma unroll
   for (int f = 0; f < FIT_F; ++f) acc[f] = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float4* p = reinterpret_cast<const float4*>(table + (size_t)c.idx[k] * FIT_F);
-    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const size_t e = c.idx[k];
+    const float4* p = reinterpret_cast<const float4*>(table + e * FIT_F);
+    float4 a = __ldcg(p), b = __ldcg(p + 1);
+    if (pk.enabled) {
+      const float4* mp = reinterpret_cast<const float4*>(pk.m + e * FIT_F);
+      const float4* vp = reinterpret_cast<const float4*>(pk.v + e * FIT_F);
+      float4 ma = __ldcg(mp), mb = __ldcg(mp + 1), va = __ldcg(vp), vb = __ldcg(vp + 1);
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+      if (__ldcg(pk.stamp[par] + e) == (uint32_t)pstep + 1u) {
+        const float4* gp = reinterpret_cast<const float4*>(pk.g[par] + e * FIT_F);
+        ga = __ldcg(gp);
+        gb = __ldcg(gp + 1);
+      }
+      adam1(a.x, ma.x, va.x, ga.x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(a.y, ma.y, va.y, ga.y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(a.z, ma.z, va.z, ga.z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(a.w, ma.w, va.w, ga.w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(b.x, mb.x, vb.x, gb.x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(b.y, mb.y, vb.y, gb.y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(b.z, mb.z, vb.z, gb.z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(b.w, mb.w, vb.w, gb.w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+    }
     acc[0] = fmaf(c.w[k], a.x, acc[0]); acc[1] = fmaf(c.w[k], a.y, acc[1]);
     acc[2] = fmaf(c.w[k], a.z, acc[2]); acc[3] = fmaf(c.w[k], a.w, acc[3]);
     acc[4] = fmaf(c.w[k], b.x, acc[4]); acc[5] = fmaf(c.w[k], b.y, acc[5]);
@@ -148,8 +207,14 @@ __global__ void fit_corners_kernel(GridLevels g, const float* __restrict__ coord
 }
 
 // backward of the encoding: dense-table gradient accumulation with vector atomics
+// `stamp` (optional): stamp[entry] = step + 1 marks the entries that received a gradient this step, so that the dense
+// Adam sweep reads (and re-zeroes) the gradient of touched entries only: 24 B/param of traffic instead of 32.
+// Two gradient / stamp buffers alternate by step parity: the sweep of step t consumes (and re-zeroes) buffer t & 1
+// while the backward of step t+1 already accumulates into the other one.
 __global__ void fit_grid_bwd_kernel(GridLevels g, const float* __restrict__ coords, StepRows sr, int n,
-                                    const float* __restrict__ denc, int ld_denc, float* __restrict__ gtable) {
+                                    const float* __restrict__ denc, int ld_denc, float* __restrict__ gtable0,
+                                    float* __restrict__ gtable1, uint32_t* __restrict__ stamp0,
+                                    uint32_t* __restrict__ stamp1) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * g.n_levels) return;
   const int i = t % n, l = t / n;
@@ -159,8 +224,13 @@ __global__ void fit_grid_bwd_kernel(GridLevels g, const float* __restrict__ coor
   const CornerSet c = grid_corners(g, l, xy.x, xy.y);
   const float4 a = *reinterpret_cast<const float4*>(denc + (size_t)i * ld_denc + l * FIT_F);
   const float4 b = *reinterpret_cast<const float4*>(denc + (size_t)i * ld_denc + l * FIT_F + 4);
+  const int par = stamp0 ? (sr.step() & 1) : 0;
+  float* gtable = par ? gtable1 : gtable0;
+  uint32_t* stamp = par ? stamp1 : stamp0;
+  const uint32_t mark = stamp ? (uint32_t)sr.step() + 1u : 0u;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    if (stamp) stamp[c.idx[k]] = mark;
     float* dst = gtable + (size_t)c.idx[k] * FIT_F;
     const float w = c.w[k];
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w * a.x), "f"(w * a.y), "f"(w * a.z),
@@ -308,31 +378,54 @@ __global__ void fit_loss_kernel(LossArgs a) {
 //   g' = g + wd p;  m += (g' - m)(1-b1);  v = b2 v + (1-b2) g'^2;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps)
 // step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are precomputed per step in double on the host.
 // ----------------------------------------------------------------------------------------------------
-struct AdamScalars {
-  float step_size, bc2_sqrt;
-};
+// (AdamScalars / adam1() are defined above, next to the encode kernel that also applies them.)
 
-__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float wd, float ss, float bc2s) {
-  g = fmaf(wd, p, g);
-  m = fmaf(g - m, 0.1f, m);                 // lerp(m, g, 1 - beta1), beta1 = 0.9
-  v = fmaf(v, 0.99f, 0.01f * g * g);        // beta2 = 0.99
-  const float denom = sqrtf(v) / bc2s + 1e-15f;
-  p = p - ss * (m / denom);
-}
-
-__global__ void fit_adam_table_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
-                                      float4* __restrict__ g, size_t nvec, const AdamScalars* __restrict__ sc,
-                                      const int* __restrict__ step_base, int step_off, float wd) {
-  const AdamScalars s = sc[*step_base + step_off];
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-    float4 pp = p[i], mm = m[i], vv = v[i];
-    const float4 gg = g[i];
-    adam1(pp.x, mm.x, vv.x, gg.x, wd, s.step_size, s.bc2_sqrt);
-    adam1(pp.y, mm.y, vv.y, gg.y, wd, s.step_size, s.bc2_sqrt);
-    adam1(pp.z, mm.z, vv.z, gg.z, wd, s.step_size, s.bc2_sqrt);
-    adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.bc2_sqrt);
-    p[i] = pp; m[i] = mm; v[i] = vv;
-    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+// Many short-lived CTAs (8 per SM, <= 64 registers): the sweep of step t runs on a LOW-priority stream beside the GEMM
+// chain of step t+1; when a sweep CTA retires, the block scheduler hands its slot to a waiting high-priority chain CTA.
+// (A persistent one-CTA-per-SM sweep was measured too: it cannot keep enough loads in flight to saturate HBM.)
+// (Forcing the maximum shared-memory carve-out on the small kernels was measured as well: it slows this streaming
+// kernel from 97 to 137 us and does not shorten the GEMMs.)
+constexpr int ADAM_UNROLL = 2;
+__global__ void __launch_bounds__(256, 4)
+fit_adam_table_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v, float4* __restrict__ g0,
+                      float4* __restrict__ g1, const uint32_t* __restrict__ stamp0, const uint32_t* __restrict__ stamp1,
+                      size_t nvec, const AdamScalars* __restrict__ sc, const int* __restrict__ step_base, int step_off,
+                      float wd) {
+  const int step = *step_base + step_off;
+  float4* __restrict__ g = (step & 1) ? g1 : g0;
+  const uint32_t* __restrict__ stamp = (step & 1) ? stamp1 : stamp0;
+  const AdamScalars s = sc[step];
+  const uint32_t mark = (uint32_t)step + 1u;
+  // grid-stride: all CTAs advance one contiguous front together, which spreads the traffic evenly over the HBM channels
+  // (giving each CTA its own contiguous slice was measured: 133 us instead of 97 us -- channel imbalance)
+  const size_t hi = nvec;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += ADAM_UNROLL * stride) {
+    float4 pp[ADAM_UNROLL], mm[ADAM_UNROLL], vv[ADAM_UNROLL], gg[ADAM_UNROLL];
+    bool ok[ADAM_UNROLL], touched[ADAM_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ADAM_UNROLL; ++u) {
+      const size_t i = i0 + u * stride;
+      ok[u] = i < hi;
+      touched[u] = ok[u] && __ldg(stamp + (i >> 1)) == mark;  // entry = 8 floats = 2 float4
+      if (ok[u]) { pp[u] = p[i]; mm[u] = m[i]; vv[u] = v[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < ADAM_UNROLL; ++u) {
+      const size_t i = i0 + u * stride;
+      gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (touched[u]) { gg[u] = g[i]; g[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+#pragma unroll
+    for (int u = 0; u < ADAM_UNROLL; ++u) {
+      if (!ok[u]) continue;
+      const size_t i = i0 + u * stride;
+      adam1(pp[u].x, mm[u].x, vv[u].x, gg[u].x, wd, s.step_size, s.inv_bc2_sqrt);
+      adam1(pp[u].y, mm[u].y, vv[u].y, gg[u].y, wd, s.step_size, s.inv_bc2_sqrt);
+      adam1(pp[u].z, mm[u].z, vv[u].z, gg[u].z, wd, s.step_size, s.inv_bc2_sqrt);
+      adam1(pp[u].w, mm[u].w, vv[u].w, gg[u].w, wd, s.step_size, s.inv_bc2_sqrt);
+      p[i] = pp[u]; m[i] = mm[u]; v[i] = vv[u];
+    }
   }
 }
 
@@ -350,10 +443,10 @@ __global__ void fit_adam_small_kernel(float4* __restrict__ p, float4* __restrict
     const AdamScalars s = is_r ? sc_res[step] : sc_main[step];
     float4 pp = p[i], mm = m[i], vv = v[i];
     const float4 gg = g[i];
-    adam1(pp.x, mm.x, vv.x, gg.x, wd, s.step_size, s.bc2_sqrt);
-    adam1(pp.y, mm.y, vv.y, gg.y, wd, s.step_size, s.bc2_sqrt);
-    adam1(pp.z, mm.z, vv.z, gg.z, wd, s.step_size, s.bc2_sqrt);
-    adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.bc2_sqrt);
+    adam1(pp.x, mm.x, vv.x, gg.x, wd, s.step_size, s.inv_bc2_sqrt);
+    adam1(pp.y, mm.y, vv.y, gg.y, wd, s.step_size, s.inv_bc2_sqrt);
+    adam1(pp.z, mm.z, vv.z, gg.z, wd, s.step_size, s.inv_bc2_sqrt);
+    adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.inv_bc2_sqrt);
     p[i] = pp; m[i] = mm; v[i] = vv;
     g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!is_g) {  // GEMM operand planes of the weights
@@ -412,7 +505,13 @@ struct Fit {
   Seg W1, b1, W2, b2, G, R1, rb1, R2, rb2, R3, rb3;
   int n_small = 0;
   // device memory
-  float *tp = nullptr, *tm = nullptr, *tv = nullptr, *tg = nullptr;
+  float *tp = nullptr, *tm = nullptr, *tv = nullptr;
+  float* tg[2] = {nullptr, nullptr};          // dense gradient of the table, by step parity
+  uint32_t* tstamp[2] = {nullptr, nullptr};   // [n_entries] step + 1 of the last gradient written, by step parity
+  cudaStream_t sD = nullptr;                   // stream of the pipelined table sweep
+  bool sweep_pending = false;                  // a sweep has been enqueued on sD and not yet joined
+  bool enc_ready = false;                      // f->enc already holds the encoding of the next step
+  bool pipeline = false;                       // software-pipelined table sweep (see fit_enqueue_step)
   float *sp = nullptr, *sm = nullptr, *sv = nullptr, *sg = nullptr;
   float* wsplit = nullptr;  // [2][n_small] TF32 hi / lo planes of the small params (x3 GEMM operands)
   // activations: GEMM operands are stored as two fp32 planes (hi, lo), plane stride = bsz * ld
@@ -437,8 +536,10 @@ struct Fit {
   cudaGraphExec_t graph1 = nullptr, graph2 = nullptr;
   int graph_steps = 0;
   long long graph1_nodes = 0, graph2_nodes = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // main stream of a step (critical path)
+  cudaStream_t sB = nullptr, sC = nullptr;  // side streams: independent GEMM chains run concurrently with the main one
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaEvent_t ev[12] = {};
   // query workspace
   int q_cap = 0;
   float *q_enc = nullptr, *q_h1 = nullptr, *q_raw = nullptr, *q_r1 = nullptr, *q_r2 = nullptr;
@@ -467,9 +568,19 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
     if (prc) return prc;
   }
   Fit* f = new Fit();
-  DVT_CUDA_OK(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;  // (numerically lower = higher priority)
+  DVT_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->stream, cudaStreamNonBlocking, prio_hi));
+  DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sB, cudaStreamNonBlocking, prio_hi));
+  DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sC, cudaStreamNonBlocking, prio_hi));
+  DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sD, cudaStreamNonBlocking, prio_lo));  // the sweep yields to the chain
+  for (auto& e : f->ev) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
   DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_out, cudaEventDisableTiming));
+  {
+    const char* pe = getenv("DVT_FIT_PIPELINE");
+    f->pipeline = pe && pe[0] == '1';
+  }
   f->C = C; f->gh = gh; f->gw = gw; f->hw = gh * gw; f->bsz = bsz; f->Lf = n_levels * FIT_F;
   f->grid.n_levels = n_levels;
   for (int l = 0; l < n_levels; ++l) {
@@ -489,7 +600,8 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   int rc = 0;
   auto A = [&](void** p, size_t bytes) { if (!rc) rc = fit_alloc(f, p, bytes); };
   A((void**)&f->tp, f->n_table * 4); A((void**)&f->tm, f->n_table * 4); A((void**)&f->tv, f->n_table * 4);
-  A((void**)&f->tg, f->n_table * 4);
+  A((void**)&f->tg[0], f->n_table * 4); A((void**)&f->tg[1], f->n_table * 4);
+  A((void**)&f->tstamp[0], f->n_table / FIT_F * 4); A((void**)&f->tstamp[1], f->n_table / FIT_F * 4);
   A((void**)&f->sp, (size_t)off * 4); A((void**)&f->sm, (size_t)off * 4); A((void**)&f->sv, (size_t)off * 4);
   A((void**)&f->sg, (size_t)off * 4); A((void**)&f->wsplit, (size_t)off * 8);
   const size_t n = bsz;
@@ -521,6 +633,10 @@ void fit_destroy(Fit* f) {
   if (!f) return;
   fit_drop_graphs(f);
   if (f->stream) cudaStreamDestroy(f->stream);
+  if (f->sB) cudaStreamDestroy(f->sB);
+  if (f->sC) cudaStreamDestroy(f->sC);
+  if (f->sD) cudaStreamDestroy(f->sD);
+  for (auto& e : f->ev) if (e) cudaEventDestroy(e);
   if (f->ev_in) cudaEventDestroy(f->ev_in);
   if (f->ev_out) cudaEventDestroy(f->ev_out);
   for (void* p : f->owned) cudaFree(p);
@@ -619,8 +735,8 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   if (num_iters != f->num_iters) {
     cudaFree(f->idx); cudaFree(f->sc_main); cudaFree(f->sc_res); cudaFree(f->losses);
     f->idx = nullptr; f->sc_main = f->sc_res = nullptr; f->losses = nullptr;
-    DVT_CUDA_OK(cudaMalloc(&f->idx, (size_t)num_iters * f->bsz * 4));
-    DVT_CUDA_OK(cudaMalloc(&f->sc_main, (size_t)num_iters * sizeof(AdamScalars)));
+    DVT_CUDA_OK(cudaMalloc(&f->idx, (size_t)(num_iters + 1) * f->bsz * 4));
+    DVT_CUDA_OK(cudaMalloc(&f->sc_main, (size_t)(num_iters + 1) * sizeof(AdamScalars)));
     DVT_CUDA_OK(cudaMalloc(&f->sc_res, (size_t)num_iters * sizeof(AdamScalars)));
     DVT_CUDA_OK(cudaMalloc(&f->losses, (size_t)num_iters * 5 * 4));
     fit_drop_graphs(f);
@@ -629,6 +745,10 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   if (freeze_step != f->freeze_step) fit_drop_graphs(f);
   f->num_iters = num_iters; f->freeze_step = freeze_step;
   DVT_CUDA_OK(cudaMemcpy(f->idx, idx_host, (size_t)num_iters * f->bsz * 4, cudaMemcpyHostToDevice));
+  DVT_CUDA_OK(cudaMemset(f->idx + (size_t)num_iters * f->bsz, 0, (size_t)f->bsz * 4));
+  // the Adam scalar tables also get read one past the end by the (unused) encode of step num_iters - handled by
+  // clamping below: allocate one extra element
+
   std::vector<AdamScalars> a(num_iters), b(num_iters);
   for (int s = 0; s < num_iters; ++s) {
     double lrs;  // dvt/utils/misc.py:306-322
@@ -636,13 +756,13 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
     else lrs = min_lr + ((double)lr - min_lr) * 0.5 * (1.0 + cos(M_PI * (s - warmup_iters) / (double)(num_iters - warmup_iters)));
     const int t = s + 1;
     a[s].step_size = (float)(lrs / (1.0 - pow(0.9, t)));
-    a[s].bc2_sqrt = (float)sqrt(1.0 - pow(0.99, t));
+    a[s].inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(0.99, t)));
     const int tr = s - freeze_step;  // residual MLP: first update at s = freeze_step + 1 has t = 1
     if (tr >= 1) {
       b[s].step_size = (float)(lrs / (1.0 - pow(0.9, tr)));
-      b[s].bc2_sqrt = (float)sqrt(1.0 - pow(0.99, tr));
+      b[s].inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(0.99, tr)));
     } else {
-      b[s].step_size = 0.f; b[s].bc2_sqrt = 1.f;
+      b[s].step_size = 0.f; b[s].inv_bc2_sqrt = 1.f;
     }
   }
   DVT_CUDA_OK(cudaMemcpy(f->sc_main, a.data(), a.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
@@ -650,7 +770,12 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   DVT_CUDA_OK(cudaMemset(f->losses, 0, (size_t)num_iters * 5 * 4));
   DVT_CUDA_OK(cudaMemset(f->step_base, 0, 4));
   DVT_CUDA_OK(cudaMemset(f->tm, 0, f->n_table * 4)); DVT_CUDA_OK(cudaMemset(f->tv, 0, f->n_table * 4));
-  DVT_CUDA_OK(cudaMemset(f->tg, 0, f->n_table * 4));
+  for (int q = 0; q < 2; ++q) {
+    DVT_CUDA_OK(cudaMemset(f->tg[q], 0, f->n_table * 4));
+    DVT_CUDA_OK(cudaMemset(f->tstamp[q], 0, f->n_table / FIT_F * 4));
+  }
+  f->enc_ready = false;
+  f->sweep_pending = false;
   DVT_CUDA_OK(cudaMemset(f->sm, 0, (size_t)f->n_small * 4)); DVT_CUDA_OK(cudaMemset(f->sv, 0, (size_t)f->n_small * 4));
   DVT_CUDA_OK(cudaMemset(f->sg, 0, (size_t)f->n_small * 4));
   fit_split_kernel<<<256, 256>>>(f->sp, f->wsplit, (size_t)f->n_small);
@@ -694,13 +819,45 @@ static int fit_dgrad(Op dY, int M, int Nout, Op W, int Kin, const float* Hmask, 
 static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb, cudaStream_t st, int impl) {
   GemmEpi e;
   e.out = gW; e.ldo = Kin; e.out_mode = OUT_F32_ATOMIC; e.last_col_out = gb;
-  int kb = (n + 31) / 32;
-  int splits = kb >= 64 ? 8 : kb >= 16 ? 4 : 1;
+  // split-K so that (output tiles x splits) fills the SMs once: tiles are 128 x 64, k-blocks 32 samples
+  const int kb = (n + 31) / 32;
+  const int tiles = ((Nout + 127) / 128) * ((Kin + 1 + 63) / 64);
+  int splits = std::max(1, std::min(num_sms() / std::max(tiles, 1), kb / 4));
   GemmShape s{Nout, Kin + 1, n, splits};
   s.a_mn = 1; s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = X.plane;
   return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
 }
 
+static PeekArgs fit_peek_args(const Fit* f, bool enabled) {
+  PeekArgs pk;
+  pk.m = f->tm; pk.v = f->tv; pk.g[0] = f->tg[0]; pk.g[1] = f->tg[1];
+  pk.stamp[0] = f->tstamp[0]; pk.stamp[1] = f->tstamp[1];
+  pk.sc = f->sc_main; pk.wd = f->wd; pk.enabled = enabled ? 1 : 0;
+  return pk;
+}
+
+// Encodes step (*step_base + step_off) into f->enc.  peek: the table sweep of the previous step is still pending.
+static int fit_enqueue_encode(Fit* f, int step_off, bool peek, cudaStream_t st) {
+  const int n = f->bsz;
+  const StepRows sr{f->idx, f->step_base, step_off};
+  const int tb = 256, blocks = (n * f->grid.n_levels + tb - 1) / tb;
+  fit_encode_kernel<<<blocks, tb, 0, st>>>(f->grid, f->tp, f->coords, sr, n, f->enc, f->ld_enc, (size_t)n * f->ld_enc,
+                                           fit_peek_args(f, peek));
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DVT_OK;
+}
+
+// One optimisation step.  Default (f->pipeline == false): encode, GEMM chain, loss, backward, then the dense table sweep,
+// all ordered on the main stream with the independent GEMM chains on side streams.
+// Experimental software-pipelined schedule (f->pipeline == true; exact, parity-tested, but not yet faster because the
+// one-wave sweep leaves no SM slots for the 216 KB GEMM CTAs -- see DESIGN.md):
+//   main stream : GEMM h1, GEMM F, [join residual fwd], loss, dgrad, dgrad, grid backward, [join side chains],
+//                 join sweep(t-1), encode(t+1) with Adam(t) applied on the fly, fork sweep(t)
+//   side B / C  : weight-gradient GEMMs, residual MLP forward / backward, Adam(small params)
+//   side D      : dense table sweep of step t, running beside the whole main chain of step t+1
+// Precondition: f->enc holds the encoding of step t.  Postcondition: f->enc holds the encoding of step t+1 and
+// sweep(t) is pending on sD.
 static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, int impl) {
   const int n = f->bsz, C = f->C, H1 = C / 2, Hr = C / 4, Lf = f->Lf;
   const StepRows sr{f->idx, f->step_base, step_off};
@@ -714,21 +871,31 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   const Op enc{f->enc, f->ld_enc, p_enc}, h1{f->h1, f->ld_h1, p_h1}, dpred{f->dpred, C, p_nc}, dh1{f->dh1, H1, p_nh};
   const Op rawb{f->rawb, f->ld_raw, p_raw}, r1{f->r1, f->ld_r, p_r}, r2{f->r2, f->ld_r, p_r};
   const Op dR{f->dR, C, p_nc}, dr2{f->dr2, Hr, p_nr}, dr1{f->dr1, Hr, p_nr};
+  cudaStream_t sB = f->sB, sC = f->sC, sD = f->sD;
+  auto fork = [&](cudaStream_t to, cudaEvent_t e) -> int {
+    DVT_CUDA_OK(cudaEventRecord(e, st));
+    DVT_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
+    return DVT_OK;
+  };
+  auto join = [&](cudaStream_t from, cudaEvent_t e) -> int {
+    DVT_CUDA_OK(cudaEventRecord(e, from));
+    DVT_CUDA_OK(cudaStreamWaitEvent(st, e, 0));
+    return DVT_OK;
+  };
   // ---- forward ----
-  fit_encode_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->tp, f->coords, sr, n, f->enc, f->ld_enc, p_enc);
-  DVT_CUDA_OK(cudaGetLastError());
-  count_launch();
-  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl));
-  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl));
+  if (!f->pipeline) FIT_RC(fit_enqueue_encode(f, step_off, /*peek=*/false, st));  // else f->enc is already this step's
   if (phase2) {
-    fit_gather_rows_kernel<<<n, 192, 0, st>>>(f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw);
+    FIT_RC(fork(sB, f->ev[0]));
+    fit_gather_rows_kernel<<<n, 192, 0, sB>>>(f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw);
     DVT_CUDA_OK(cudaGetLastError());
     count_launch();
-  count_launch();
-    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, st, impl));
-    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, st, impl));
-    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, st, impl));
+    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl));
+    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl));
+    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl));
   }
+  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl));
+  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl));
+  if (phase2) FIT_RC(join(sB, f->ev[1]));
   // ---- loss + d pred ----
   LossArgs la;
   la.bank = f->bank; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
@@ -737,34 +904,76 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   fit_loss_kernel<<<(n * 32 + tb - 1) / tb, tb, 0, st>>>(la);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  // ---- backward: field MLP + grid ----
-  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl));
-  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, st, impl));
-  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, st, impl));
+  // ---- backward ----
+  FIT_RC(fork(sB, f->ev[2]));
+  if (phase2) FIT_RC(fork(sC, f->ev[3]));
+  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl));          // side B
+  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl));  // main
+  FIT_RC(fork(sB, f->ev[4]));  // dh1 ready
+  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl));           // side B (reads enc)
   FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl));
-  fit_grid_bwd_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->coords, sr, n, f->denc, Lf, f->tg);
+  fit_grid_bwd_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->coords, sr, n, f->denc, Lf, f->tg[0], f->tg[1],
+                                                 f->tstamp[0], f->tstamp[1]);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  // ---- backward: residual MLP ----
-  if (phase2) {
-    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, st, impl));
-    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, st, impl));
-    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, st, impl));
-    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, st, impl));
-    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, st, impl));
+  if (phase2) {                                                                              // side C
+    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, sC, impl));
+    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sC, impl));
+    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, sC, impl));
+    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sC, impl));
+    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl));
+    FIT_RC(join(sC, f->ev[5]));
   }
-  // ---- Adam ----
-  fit_adam_table_kernel<<<num_sms() * 8, 256, 0, st>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv, (float4*)f->tg,
-                                                        f->n_table / 4, f->sc_main, f->step_base, step_off, f->wd);
-  DVT_CUDA_OK(cudaGetLastError());
-  count_launch();
+  FIT_RC(join(sB, f->ev[6]));  // all small-parameter gradients complete; enc no longer read by a wgrad
+  if (!f->pipeline) {
+    // ---- sequential schedule: dense table sweep on the main stream, Adam(small) beside it ----
+    FIT_RC(fork(sB, f->ev[7]));
+    const int nv0 = f->n_small / 4;
+    fit_adam_small_kernel<<<(nv0 + 255) / 256, 256, 0, sB>>>(
+        (float4*)f->sp, (float4*)f->sm, (float4*)f->sv, (float4*)f->sg, f->wsplit, nv0, f->G.off / 4,
+        (f->G.off + r8(f->G.rows * f->G.cols)) / 4, f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res, f->step_base,
+        step_off, f->freeze_step, f->wd);
+    DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
+    fit_adam_table_kernel<<<num_sms() * 8, 256, 0, st>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
+                                                          (float4*)f->tg[0], (float4*)f->tg[1], f->tstamp[0],
+                                                          f->tstamp[1], f->n_table / 4, f->sc_main, f->step_base, step_off,
+                                                          f->wd);
+    DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
+    FIT_RC(join(sB, f->ev[8]));
+    return DVT_OK;
+  }
+  // ---- the previous step's table sweep must be complete before its state is read / the next sweep starts ----
+  if (f->sweep_pending) FIT_RC(join(sD, f->ev[9]));
+  // ---- Adam(small) beside the encode of the NEXT step (Adam step t of the table applied on the fly) ----
+  FIT_RC(fork(sB, f->ev[7]));
   const int nv = f->n_small / 4;
-  fit_adam_small_kernel<<<(nv + 255) / 256, 256, 0, st>>>(
+  fit_adam_small_kernel<<<(nv + 255) / 256, 256, 0, sB>>>(
       (float4*)f->sp, (float4*)f->sm, (float4*)f->sv, (float4*)f->sg, f->wsplit, nv, f->G.off / 4,
       (f->G.off + r8(f->G.rows * f->G.cols)) / 4, f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res, f->step_base,
       step_off, f->freeze_step, f->wd);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
+  FIT_RC(fit_enqueue_encode(f, step_off + 1, /*peek=*/true, st));
+  FIT_RC(join(sB, f->ev[8]));
+  // ---- dense table sweep of this step: forked, joined by the next step (or by fit_sync_sweep) ----
+  FIT_RC(fork(sD, f->ev[10]));
+  fit_adam_table_kernel<<<num_sms() * 8, 256, 0, sD>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
+                                                        (float4*)f->tg[0], (float4*)f->tg[1], f->tstamp[0], f->tstamp[1],
+                                                        f->n_table / 4, f->sc_main, f->step_base, step_off, f->wd);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  f->sweep_pending = true;
+  return DVT_OK;
+}
+
+// Waits (on `st`) for the pending table sweep.
+static int fit_sync_sweep(Fit* f, cudaStream_t st) {
+  if (!f->sweep_pending) return DVT_OK;
+  DVT_CUDA_OK(cudaEventRecord(f->ev[9], f->sD));
+  DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev[9], 0));
+  f->sweep_pending = false;
   return DVT_OK;
 }
 
@@ -773,7 +982,9 @@ static int fit_capture(Fit* f, bool phase2, int steps, cudaStream_t st, int impl
   const long long before = launch_count();
   DVT_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   int rc = DVT_OK;
+  f->sweep_pending = false;  // graphs start and end with the table up to date
   for (int i = 0; i < steps && rc == DVT_OK; ++i) rc = fit_enqueue_step(f, i, phase2, st, impl);
+  if (rc == DVT_OK) rc = fit_sync_sweep(f, st);  // a capture must join every forked stream
   if (rc == DVT_OK) {
     fit_advance_kernel<<<1, 1, 0, st>>>(f->step_base, steps);
     if (cudaGetLastError() != cudaSuccess) rc = DVT_ERR_CUDA;
@@ -807,6 +1018,10 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
   DVT_REQUIRE(count >= 0 && cur + count <= f->num_iters, "fit_run: %d steps from %d exceed the schedule of %d", count, cur,
               f->num_iters);
   const int end = cur + count;
+  if (f->pipeline && count > 0 && !f->enc_ready) {  // first step of a fit: plain encode, no Adam step pending
+    FIT_RC(fit_enqueue_encode(f, 0, /*peek=*/false, st));
+    f->enc_ready = true;
+  }
   if (use_graphs > 0 && use_graphs != f->graph_steps) {
     fit_drop_graphs(f);
     f->graph_steps = use_graphs;
@@ -824,6 +1039,8 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
       cur += use_graphs;
     } else {
       FIT_RC(fit_enqueue_step(f, 0, phase2, st, impl));
+      // the sweep reads the device step counter: it must finish before the counter advances
+      FIT_RC(fit_sync_sweep(f, st));
       fit_advance_kernel<<<1, 1, 0, st>>>(f->step_base, 1);
       DVT_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -831,6 +1048,7 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
       cur += 1;
     }
   }
+  FIT_RC(fit_sync_sweep(f, st));
   DVT_CUDA_OK(cudaEventRecord(f->ev_out, st));
   DVT_CUDA_OK(cudaStreamWaitEvent(caller, f->ev_out, 0));
   return DVT_OK;
@@ -864,7 +1082,7 @@ int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, i
   const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};
   fit_encode_kernel<<<(n * f->grid.n_levels + 255) / 256, 256, 0, st>>>(f->grid, f->tp, coords, sr, n, f->q_enc, f->ld_enc,
-                                                                       cap * f->ld_enc);
+                                                                       cap * f->ld_enc, fit_peek_args(f, false));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   FIT_RC(fit_linear(Op{f->q_enc, f->ld_enc, cap * f->ld_enc}, n, f->Lf, Op{f->wsplit + f->W1.off, f->Lf, wp}, H1,
@@ -928,7 +1146,8 @@ int hashgrid_bwd(int n_levels, const float* scale, const uint32_t* res, const ui
   GridLevels g;
   FIT_RC(levels_from_arrays(&g, n_levels, scale, res, size, offset, hashed));
   const StepRows sr{nullptr, nullptr, 0};
-  fit_grid_bwd_kernel<<<(n * n_levels + 255) / 256, 256, 0, st>>>(g, coords, sr, n, dout, n_levels * FIT_F, gtable);
+  fit_grid_bwd_kernel<<<(n * n_levels + 255) / 256, 256, 0, st>>>(g, coords, sr, n, dout, n_levels * FIT_F, gtable, gtable,
+                                                                  nullptr, nullptr);
   DVT_CUDA_OK(cudaGetLastError());
   return DVT_OK;
 }

@@ -1,9 +1,10 @@
 // TN GEMM on 5th-gen tensor cores: C[M,N] = A[M,K] * B[N,K]^T with fused epilogues.
 //
-// One persistent CTA per SM, 6 warps:
-//   warp 0      TMA producer   (A: 128 x 128B box, B: BN x 128B box, SWIZZLE_128B, 4-stage mbarrier ring)
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer   (A: 128 x 128B box, B: BN x 128B box, SWIZZLE_128B, 3-5 stage mbarrier ring)
 //   warp 1      MMA issuer     (lane 0 issues tcgen05.mma M=128 N=BN K=16/8; accumulators in TMEM, 2 stages)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced stores)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced stores;
+//               two warps per TMEM lane quadrant take alternating 32-column chunks; 4 warps in the x3 kernels)
 // K tails, M tails and N tails are handled by TMA zero-fill plus masking in the epilogue.
 //
 // Used for: patch-embed, QKV, attention out-proj, MLP fc1/fc2 (reference: timm VisionTransformer reached from
@@ -19,15 +20,19 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int KB_BYTES = 128;  // bytes of K per pipeline stage row (= one 128B swizzle atom)
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int GEMM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+// 8 epilogue warps per CTA (two per TMEM lane quadrant, alternating 32-column chunks: twice the ALU throughput and
+// memory-level parallelism of one warp per scheduler).  The x3 (fit) kernels use 128x64 tiles: their problems are small
+// (M = 2048), so narrower tiles mean more CTAs, half the MMA time per k-block and a one-chunk-per-warp epilogue.
+constexpr int epi_warps(bool) { return 8; }
 constexpr int SCR_PITCH = 36;  // floats; 16B-aligned rows, conflict-free for the access pattern below
 
 template <int BN, int STAGES, bool X3 = false>
 struct GemmSmem {
+  static constexpr int EW = epi_warps(X3);
+  static constexpr int THREADS = 32 * (2 + EW);
   static constexpr int A_BYTES = BM * KB_BYTES * (X3 ? 2 : 1);  // x3: hi plane then lo plane
   static constexpr int B_BYTES = BN * KB_BYTES * (X3 ? 2 : 1);
-  static constexpr int SCR_BYTES = NUM_EPI_WARPS * 32 * SCR_PITCH * 4;
+  static constexpr int SCR_BYTES = EW * 32 * SCR_PITCH * 4;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
   static constexpr int OFF_SCR = OFF_B + STAGES * B_BYTES;
@@ -37,8 +42,26 @@ struct GemmSmem {
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + alignment slack
 };
 
+// Ragged-N tail of one 32x32 chunk (last chunk of N = 385, 129, ...): rare, so its loops stay rolled (unrolled it
+// made every kernel 130 KB; an out-of-line call was tried too and cost 30 % on the big GEMMs through ABI spills).
+__device__ __forceinline__ void epi_scalar_tail(const GemmEpi& e, const GemmShape& s, const float* scr, int lane, int m0,
+                                             int n, bool has_k) {
+#pragma unroll 1
+  for (int jj = 0; jj < 8; ++jj) {
+    const int i = (lane >> 3) + 4 * jj;
+    const int m = m0 + 4 * jj;
+    if (m >= s.M) continue;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      if (n + q >= s.N) break;
+      const float x = scr[i * SCR_PITCH + (lane & 7) * 4 + q];
+      epi_post1(e, m, n + q, epi_pre(e, m, n + q, has_k ? x : 0.0f));
+    }
+  }
+}
+
 template <int BN, int STAGES, bool TF32, bool A_MN, bool B_MN, bool X3 = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmSmem<BN, STAGES, X3>::THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape s,
                   GemmEpi e) {
   static_assert(!X3 || TF32, "x3 is a TF32 mode");
@@ -66,6 +89,15 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  auto stampt = [&](int slot) {
+    if (e.debug_ts && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      e.debug_ts[slot] = t;
+    }
+  };
+  if (threadIdx.x == 0) stampt(0);  // kernel entry
+  if (threadIdx.x == 0 && e.debug_ts && blockIdx.x == 0) e.debug_ts[14] = (unsigned long long)clock64();
 
   const int tiles_m = (s.M + BM - 1) / BM;
   const int tiles_n = (s.N + BN - 1) / BN;
@@ -82,7 +114,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], NUM_EPI_WARPS * 32);
+      mbar_init(&tempty[i], L::EW * 32);
     }
     fence_mbar_init();
   }
@@ -94,6 +126,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stampt(1);  // setup done (barriers, TMEM)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -168,6 +201,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
+          if (kb == kb0) stampt(2);  // first operands landed
           // K-major: rows of 128 B (one swizzle atom of K), 8-row groups 1024 B apart; K advances 32 B per MMA.
           // MN-major (bf16): tile = [MN/64 atoms][BK k-rows][64 mn]; atoms BK*128 B apart (LBO), 8-k groups 1024 B
           // apart (SBO); K advances 16 rows = 2048 B per MMA.
@@ -208,6 +242,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         umma_commit(&tfull[as]);  // accumulator complete
+        stampt(3);                // all MMAs issued
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -218,6 +253,8 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    constexpr int CSTEP = L::EW / 4;       // warps sharing a quadrant
+    const int c_first = ew >> 2;           // ... take alternating 32-column chunks
     float* scr = scr_all + ew * 32 * SCR_PITCH;
     int as = 0;
     uint32_t aphase = 0;
@@ -230,13 +267,14 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool has_k = kb0 < kb_total;
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
+      if (ew == 0 && lane == 0) stampt(4);  // accumulator ready, epilogue starts
       const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_first; c < BN / 32; c += CSTEP) {
         uint32_t r[32];
         tmem_ld_32x32(taddr_row + c * 32, r);
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {
+        if (c + CSTEP >= BN / 32) {  // this warp's last read of the accumulator stage
           tc_fence_before();
           mbar_arrive(&tempty[as]);
         }
@@ -300,19 +338,10 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         } else {
           // ---------------- ragged N tail: scalar path ----------------
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int i = (lane >> 3) + 4 * jj;
-            const int m = m0 + 4 * jj;
-            const float4 x = *reinterpret_cast<const float4*>(scr + i * SCR_PITCH + col4);
-            if (m >= s.M) continue;
-            const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (n + q < s.N) epi_post1(e, m, n + q, epi_pre(e, m, n + q, has_k ? xs[q] : 0.0f));
-          }
+          epi_scalar_tail(e, s, scr, lane, m0, n, has_k);
         }
         __syncwarp();
+        if (ew == 0 && lane == 0) stampt(8 + (c & 7));  // chunk done (profiling aid)
       }
       if (++as == 2) {
         as = 0;
@@ -321,12 +350,15 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
+  if (warp == 2 && lane == 0) stampt(5);  // first epilogue warp done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) stampt(6);  // kernel exit
+  if (threadIdx.x == 0 && e.debug_ts && blockIdx.x == 0) e.debug_ts[15] = (unsigned long long)clock64();
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -378,7 +410,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s
   auto kern = gemm_tn_tc_kernel<BN, STAGES, TF32, A_MN, B_MN, X3>;
   const int tiles = ((s.M + BM - 1) / BM) * ((s.N + BN - 1) / BN) * s.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, s, e);
+  kern<<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, s, e);
   count_launch();
   DVT_CUDA_OK(cudaGetLastError());
   return DVT_OK;
@@ -398,17 +430,17 @@ int gemm_prepare() {
   static bool done = false;
   if (done) return DVT_OK;
   int rc;
-  if ((rc = prep_one<256, 4, true, false, false>())) return rc;
-  if ((rc = prep_one<128, 6, true, false, false>())) return rc;
-  if ((rc = prep_one<256, 4, false, true, true>())) return rc;
-  if ((rc = prep_one<128, 6, false, true, true>())) return rc;
-  if ((rc = prep_one<256, 4, false, false, true>())) return rc;
-  if ((rc = prep_one<128, 6, false, false, true>())) return rc;
-  if ((rc = prep_one<256, 4, false, false, false>())) return rc;
-  if ((rc = prep_one<128, 6, false, false, false>())) return rc;
-  if ((rc = prep_one<128, 3, true, false, false, true>())) return rc;
-  if ((rc = prep_one<128, 3, true, false, true, true>())) return rc;
-  if ((rc = prep_one<128, 3, true, true, true, true>())) return rc;
+  if ((rc = prep_one<256, 3, true, false, false>())) return rc;
+  if ((rc = prep_one<128, 5, true, false, false>())) return rc;
+  if ((rc = prep_one<256, 3, false, true, true>())) return rc;
+  if ((rc = prep_one<128, 5, false, true, true>())) return rc;
+  if ((rc = prep_one<256, 3, false, false, true>())) return rc;
+  if ((rc = prep_one<128, 5, false, false, true>())) return rc;
+  if ((rc = prep_one<256, 3, false, false, false>())) return rc;
+  if ((rc = prep_one<128, 5, false, false, false>())) return rc;
+  if ((rc = prep_one<64, 3, true, false, false, true>())) return rc;
+  if ((rc = prep_one<64, 3, true, false, true, true>())) return rc;
+  if ((rc = prep_one<64, 3, true, true, true, true>())) return rc;
   done = true;
   return DVT_OK;
 }
@@ -466,11 +498,11 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
     else rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.K, (uint64_t)s.M, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, BM, 2);
     if (rc3) return rc3;
     if (s.b_mn) rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.N, (uint64_t)s.K, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 32, 2, true);
-    else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 128, 2);
+    else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 64, 2);
     if (rc3) return rc3;
-    if (s.a_mn) return launch_tc<128, 3, true, true, true, true>(tA, tB, s, epi, stream);
-    if (s.b_mn) return launch_tc<128, 3, true, false, true, true>(tA, tB, s, epi, stream);
-    return launch_tc<128, 3, true, false, false, true>(tA, tB, s, epi, stream);
+    if (s.a_mn) return launch_tc<64, 3, true, true, true, true>(tA, tB, s, epi, stream);
+    if (s.b_mn) return launch_tc<64, 3, true, false, true, true>(tA, tB, s, epi, stream);
+    return launch_tc<64, 3, true, false, false, true>(tA, tB, s, epi, stream);
   }
   DVT_REQUIRE(dtype == TMAP_BF16 || (!s.a_mn && !s.b_mn), "gemm: MN-major operands are implemented for bf16 only");
   DVT_REQUIRE(!(s.a_mn && !s.b_mn), "gemm: A MN-major with B K-major is not instantiated");
@@ -489,16 +521,16 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
   else rc = make_tmap_2d(&tmB, B, dtype, (uint64_t)s.N, (uint64_t)s.K, (uint64_t)ldb * elem, wide ? 256 : 128, bk);
   if (rc) return rc;
   if (dtype == TMAP_F32)
-    return wide ? launch_tc<256, 4, true, false, false>(tmA, tmB, s, epi, stream)
-                : launch_tc<128, 6, true, false, false>(tmA, tmB, s, epi, stream);
+    return wide ? launch_tc<256, 3, true, false, false>(tmA, tmB, s, epi, stream)
+                : launch_tc<128, 5, true, false, false>(tmA, tmB, s, epi, stream);
   if (s.a_mn)
-    return wide ? launch_tc<256, 4, false, true, true>(tmA, tmB, s, epi, stream)
-                : launch_tc<128, 6, false, true, true>(tmA, tmB, s, epi, stream);
+    return wide ? launch_tc<256, 3, false, true, true>(tmA, tmB, s, epi, stream)
+                : launch_tc<128, 5, false, true, true>(tmA, tmB, s, epi, stream);
   if (s.b_mn)
-    return wide ? launch_tc<256, 4, false, false, true>(tmA, tmB, s, epi, stream)
-                : launch_tc<128, 6, false, false, true>(tmA, tmB, s, epi, stream);
-  return wide ? launch_tc<256, 4, false, false, false>(tmA, tmB, s, epi, stream)
-              : launch_tc<128, 6, false, false, false>(tmA, tmB, s, epi, stream);
+    return wide ? launch_tc<256, 3, false, false, true>(tmA, tmB, s, epi, stream)
+                : launch_tc<128, 5, false, false, true>(tmA, tmB, s, epi, stream);
+  return wide ? launch_tc<256, 3, false, false, false>(tmA, tmB, s, epi, stream)
+              : launch_tc<128, 5, false, false, false>(tmA, tmB, s, epi, stream);
 }
 
 }  // namespace dvt

@@ -31,6 +31,7 @@ struct GemmEpi {
   void* out = nullptr;
   int ldo = 0;
   size_t out_plane = 0;               // OUT_F32_SPLIT: element offset of the lo plane
+  unsigned long long* debug_ts = nullptr;  // optional [8]: globaltimer (ns) milestones of CTA 0 (profiling aid)
   int last_col_n = -1;                // = N-1 when last_col_out is set (filled in by launch_gemm)
   float* last_col_out = nullptr;      // OUT_F32_ATOMIC only: column N-1 is accumulated into last_col_out[m] instead
                                       // (bias gradient through a ones column in the B operand)

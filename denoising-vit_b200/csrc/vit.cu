@@ -61,6 +61,10 @@ static int dev_alloc(Vit* v, void** p, size_t bytes) {
 
 int vit_create(Vit** out, int embed, int depth, int heads, int patch, int mlp_hidden, int swiglu, int layerscale,
                int prefix, float ln_eps) {
+  {
+    int prc = gemm_prepare();
+    if (prc) return prc;
+  }
   DVT_REQUIRE(embed == heads * 64, "vit: only head_dim 64 is supported (embed=%d heads=%d)", embed, heads);
   DVT_REQUIRE(embed % 8 == 0 && mlp_hidden % 8 == 0 && depth > 0 && patch > 0 && prefix >= 1, "vit: bad config");
   Vit* v = new Vit();

@@ -22,6 +22,7 @@ SIGNATURES = {
     "dvt_device_error": (c_int, [POINTER(c_uint)]),
     "dvt_set_debug_impl": (c_int, [c_int]),
     "dvt_launch_count": (ctypes.c_longlong, []),
+    "dvt_debug_set_timestamp_buffer": (c_int, [c_void_p]),
     "dvt_gemm_tn": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                             c_int, c_int, c_int, c_void_p]),
     "dvt_gemm_tn_residual": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -232,7 +232,8 @@ class B200VisionTransformer(nn.Module):
         return self._pos_cache[key]
 
     # ---- forward --------------------------------------------------------------------------------------
-    def _run(self, x: torch.Tensor, layer_index: int, norm: bool, all_tokens: bool) -> torch.Tensor:
+    def _run(self, x: torch.Tensor, layer_index: int, norm: bool, all_tokens: bool,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if not x.is_cuda:
             raise _lib.DvtError("dvt_b200 ViT forward needs a CUDA tensor (no CPU fallback)")
         if x.dtype not in (torch.float32, torch.bfloat16):
@@ -245,10 +246,11 @@ class B200VisionTransformer(nn.Module):
         h, w = (H - P) // stride + 1, (W - P) // stride + 1
         pos_patch, prefix_rows = self._pos_tables(h, w, x.device)
         C = self.embed_dim
-        if all_tokens:
-            out = torch.empty((B, self.num_prefix_tokens + h * w, C), device=x.device, dtype=torch.float32)
-        else:
-            out = torch.empty((B, h, w, C), device=x.device, dtype=torch.float32)
+        shape = (B, self.num_prefix_tokens + h * w, C) if all_tokens else (B, h, w, C)
+        if out is None:
+            out = torch.empty(shape, device=x.device, dtype=torch.float32)
+        else:  # caller-provided destination (e.g. a slice of the stage-1 feature bank)
+            assert tuple(out.shape) == shape and out.dtype == torch.float32 and out.is_contiguous() and out.is_cuda
         check(lib().dvt_vit_forward(self._handle, ptr(x), 0 if x.dtype == torch.bfloat16 else 1, B, H, W, stride,
                                     ptr(pos_patch), ptr(prefix_rows), layer_index, int(norm), ptr(out),
                                     int(all_tokens), cur_stream()), "dvt_vit_forward")
@@ -343,6 +345,11 @@ class PretrainedViTWrapper(nn.Module):
             transforms.Normalize(mean=a["mean"], std=a["std"]),
         ])
         return model, transformation
+
+    def extract_into(self, x: torch.Tensor, layer_index: int, out_nhwc: torch.Tensor, norm: bool = True) -> torch.Tensor:
+        """B200-only convenience used by the stage-1 pipeline: writes the [B, h, w, C] map of `layer_index` straight into
+        `out_nhwc` (a slice of the feature bank) instead of returning a fresh tensor."""
+        return self.model._run(x, layer_index, norm, all_tokens=False, out=out_nhwc)
 
     def get_intermediate_layers(self, x: torch.Tensor, n: Union[int, List[int], Tuple[int]] = 1, reshape: bool = True,
                                 return_prefix_tokens: bool = False, norm: bool = True):

@@ -45,21 +45,46 @@ class Stage1Pipeline:
 
     # ---- HP-1 ----------------------------------------------------------------------------------------------
     def extract_bank(self, views: torch.Tensor) -> torch.Tensor:
-        """views [V, 3, H, W] (cuda, or pinned host memory: copied batch by batch) -> bank [V, h, w, C] fp32 (cuda)."""
+        """views [V, 3, H, W] (cuda, or pinned host memory) -> bank [V, h, w, C] fp32 (cuda).
+        Host views are copied batch by batch on a side stream into two staging buffers, so the copy of batch k+1
+        overlaps the forward of batch k."""
         V = views.shape[0]
         if self._bank is None or self._bank.shape[0] != V:
             self._bank = torch.empty((V, self.h, self.w, self.C), device="cuda", dtype=torch.float32)
         bsz = self.cfg.extract_bsz
-        for s in range(0, V, bsz):
-            x = views[s:s + bsz]
-            if not x.is_cuda:
-                if self._stage is None or self._stage.shape[0] < x.shape[0] or self._stage.dtype != x.dtype:
-                    self._stage = torch.empty((bsz,) + tuple(views.shape[1:]), device="cuda", dtype=x.dtype)
-                dst = self._stage[:x.shape[0]]
-                dst.copy_(x, non_blocking=True)
-                x = dst
-            feats = self.vit.get_intermediate_layers(x, n=[self.layer_index], reshape=True)[-1]  # NCHW view of NHWC
-            self._bank[s:s + x.shape[0]] = feats.permute(0, 2, 3, 1)
+        starts = list(range(0, V, bsz))
+        on_host = not views.is_cuda
+        if on_host:
+            if self._stage is None or self._stage[0].shape[0] != bsz or self._stage[0].dtype != views.dtype:
+                self._stage = [torch.empty((bsz,) + tuple(views.shape[1:]), device="cuda", dtype=views.dtype) for _ in range(2)]
+                self._copy_stream = torch.cuda.Stream()
+                self._copied = [torch.cuda.Event(), torch.cuda.Event()]
+                self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            main = torch.cuda.current_stream()
+
+            def issue_copy(k):
+                s0 = starts[k]
+                n = min(bsz, V - s0)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(self._consumed[k % 2])  # staging buffer free again
+                    self._stage[k % 2][:n].copy_(views[s0:s0 + n], non_blocking=True)
+                    self._copied[k % 2].record(self._copy_stream)
+
+            for e in self._consumed:
+                e.record(main)
+            issue_copy(0)
+        for k, s0 in enumerate(starts):
+            n = min(bsz, V - s0)
+            if on_host:
+                if k + 1 < len(starts):
+                    issue_copy(k + 1)
+                main.wait_event(self._copied[k % 2])
+                x = self._stage[k % 2][:n]
+            else:
+                x = views[s0:s0 + n]
+            self.vit.extract_into(x, self.layer_index, self._bank[s0:s0 + n])  # NHWC, no NCHW round trip
+            if on_host:
+                self._consumed[k % 2].record(main)
         return self._bank
 
     # ---- HP-2 ----------------------------------------------------------------------------------------------

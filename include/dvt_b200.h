@@ -42,6 +42,9 @@ const char* dvt_last_error(void);
 int dvt_device_error(unsigned int* code_out);
 /* Number of kernels this library has launched in the calling process (CUDA-graph replays count their nodes). */
 long long dvt_launch_count(void);
+/* Profiling aid: when set (device pointer to 16 x u64, or NULL to disable), dvt_gemm_f32x3 launches record %globaltimer
+ * milestones of CTA 0: entry, setup done, first operands landed, MMAs issued, epilogue start, epilogue end, exit. */
+int dvt_debug_set_timestamp_buffer(unsigned long long* dev_buf16);
 /* Process-wide kernel implementation switch for debugging: 0 = tcgen05 tensor-core kernels (default),
  * 1 = plain SIMT reference kernels (same semantics, slow).  Also settable with DVT_GEMM_IMPL=simt. */
 int dvt_set_debug_impl(int impl);
