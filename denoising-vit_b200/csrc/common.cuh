@@ -281,7 +281,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): cheap enough for a GEMM epilogue.
 __device__ __forceinline__ float fast_erf(float x) {
   float ax = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP, no IEEE fix-up sequence
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

@@ -262,7 +262,10 @@ __global__ void fit_gather_rows_kernel(const float* __restrict__ bank, int C, St
 // losses[5] (this step's slots) accumulates: total, patch_l2, cosine, residual, residual_sparsity.
 // ----------------------------------------------------------------------------------------------------
 struct LossArgs {
-  const float* bank;        // [Nb, C] raw ViT features
+  const float* raw;         // [2 planes][n, ld_raw] raw ViT features of the sampled rows (hi / lo, gathered on a side stream:
+                            //  random 3 KB rows of a 3 GB bank are TLB misses that must not sit on the critical path)
+  int ld_raw;
+  size_t raw_plane;
   StepRows sr;              // bank rows of this step
   const float* F;           // [n, C] field output
   const float* G;           // [hw, C] shared artifact map (fp32 master)
@@ -276,101 +279,150 @@ struct LossArgs {
   float loss_scale;
 };
 
-__global__ void fit_loss_kernel(LossArgs a) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// NV = float4 per lane (ceil(C / 128)); all global loads of a row are issued before the first use.
+template <int NV, bool HAS_R>
+__global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
+  const int row_raw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= a.n) return;
-  const int C = a.C, nvec = C >> 2;
+  const bool row_ok = row_raw < a.n;       // (whole warps; the CTA still meets at the __syncthreads below)
+  const int row = row_ok ? row_raw : a.n - 1;
+  const int C = a.C, nvec = row_ok ? (a.C >> 2) : 0;  // a warp without a row loads / stores nothing
   const int br = a.sr.rows(a.n)[row];
   float* losses = a.losses + (size_t)a.sr.step() * 5;
   const int cell = br % a.hw;  // exact (r, c) of the patch inside its view: the "shared artifact coordinate"
-  const float4* raw4 = reinterpret_cast<const float4*>(a.bank + (size_t)br * C);
+  const float4* raw4 = reinterpret_cast<const float4*>(a.raw + (size_t)row * a.ld_raw);
+  const float4* raw4lo = reinterpret_cast<const float4*>(a.raw + a.raw_plane + (size_t)row * a.ld_raw);
   const float4* F4 = reinterpret_cast<const float4*>(a.F + (size_t)row * C);
   const float4* G4 = reinterpret_cast<const float4*>(a.G + (size_t)cell * C);
-  const float4* R4 = a.R ? reinterpret_cast<const float4*>(a.R + (size_t)row * C) : nullptr;
-  float4 pred[12], raw[12];
-  float dot = 0.f, pp = 0.f, rr = 0.f, sse = 0.f;
+  const float4* R4 = HAS_R ? reinterpret_cast<const float4*>(a.R + (size_t)row * C) : nullptr;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 pred[NV], raw[NV], rp[HAS_R ? NV : 1];
+  {
+    float4 f[NV], gg[NV], rl[NV];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
-      const float4 f = F4[v], gg = __ldg(G4 + v), r = __ldg(raw4 + v);
-      float4 p = make_float4(f.x + gg.x, f.y + gg.y, f.z + gg.z, f.w + gg.w);
-      if (R4) {
-        const float4 rp = R4[v];
-        p.x += rp.x; p.y += rp.y; p.z += rp.z; p.w += rp.w;
-      }
-      pred[i] = p;
-      raw[i] = r;
-      dot += p.x * r.x + p.y * r.y + p.z * r.z + p.w * r.w;
-      pp += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
-      rr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
-      const float dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z, dw = p.w - r.w;
-      sse += dx * dx + dy * dy + dz * dz + dw * dw;
+    for (int i = 0; i < NV; ++i) {  // loads only
+      const int v = lane + 32 * i;
+      const bool ok = v < nvec;
+      f[i] = ok ? F4[v] : z4;
+      gg[i] = ok ? __ldg(G4 + v) : z4;
+      raw[i] = ok ? raw4[v] : z4;
+      rl[i] = ok ? raw4lo[v] : z4;
+      if (HAS_R) rp[i] = ok ? R4[v] : z4;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      raw[i] = make_float4(raw[i].x + rl[i].x, raw[i].y + rl[i].y, raw[i].z + rl[i].z, raw[i].w + rl[i].w);  // hi + lo == raw
+      pred[i] = make_float4(f[i].x + gg[i].x, f[i].y + gg[i].y, f[i].z + gg[i].z, f[i].w + gg[i].w);
+      if (HAS_R) { pred[i].x += rp[i].x; pred[i].y += rp[i].y; pred[i].z += rp[i].z; pred[i].w += rp[i].w; }
     }
   }
-  dot = warp_sum(dot); pp = warp_sum(pp); rr = warp_sum(rr); sse = warp_sum(sse);
+  float dot = 0.f, pp = 0.f, rr = 0.f, sse = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {  // lanes beyond nvec hold zeros: they add nothing
+    const float4 p = pred[i], r = raw[i];
+    dot += p.x * r.x + p.y * r.y + p.z * r.z + p.w * r.w;
+    pp += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+    rr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+    const float dx = p.x - r.x, dy = p.y - r.y, dz = p.z - r.z, dw = p.w - r.w;
+    sse += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {  // four reductions interleaved
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    pp += __shfl_xor_sync(0xffffffffu, pp, o);
+    rr += __shfl_xor_sync(0xffffffffu, rr, o);
+    sse += __shfl_xor_sync(0xffffffffu, sse, o);
+  }
   const float np_ = fmaxf(sqrtf(pp), 1e-8f), nr_ = fmaxf(sqrtf(rr), 1e-8f);  // F.cosine_similarity eps
   const float cosv = dot / (np_ * nr_);
   const float inv_nc = 1.f / ((float)a.n * (float)C), inv_n = 1.f / (float)a.n;
   // d/dpred [ mean((p-r)^2) + 1 - mean_rows cos ] * loss_scale
   const float k_mse = 2.f * inv_nc * a.loss_scale;
-  const float k_cr = -inv_n * a.loss_scale / (np_ * nr_);   // coefficient of raw
+  const float k_cr = -inv_n * a.loss_scale / (np_ * nr_);        // coefficient of raw
   const float k_cp = inv_n * a.loss_scale * cosv / (np_ * np_);  // coefficient of pred
   float res_sq = 0.f, res_abs = 0.f;
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
-    if (v < nvec) {
-      const float4 p = pred[i], r = raw[i];
-      float4 d;
-      d.x = k_mse * (p.x - r.x) + k_cr * r.x + k_cp * p.x;
-      d.y = k_mse * (p.y - r.y) + k_cr * r.y + k_cp * p.y;
-      d.z = k_mse * (p.z - r.z) + k_cr * r.z + k_cp * p.z;
-      d.w = k_mse * (p.w - r.w) + k_cr * r.w + k_cp * p.w;
-      {
-        const float4 hi = make_float4(tf32_hi(d.x), tf32_hi(d.y), tf32_hi(d.z), tf32_hi(d.w));
-        float* dp = a.dpred + (size_t)row * C + v * 4;
-        *reinterpret_cast<float4*>(dp) = hi;
-        *reinterpret_cast<float4*>(dp + a.plane) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
-      }
-      if (a.gG) {
-        float* dst = a.gG + (size_t)cell * C + v * 4;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
-                     : "memory");
-      }
-      if (R4) {
-        // gt_residual = raw - denoised - shared = raw - (pred - R); e = R - gt = pred - raw
-        const float4 rp = R4[v];
-        const float ex = p.x - r.x, ey = p.y - r.y, ez = p.z - r.z, ew = p.w - r.w;
-        res_sq += ex * ex + ey * ey + ez * ez + ew * ew;
-        res_abs += fabsf(rp.x) + fabsf(rp.y) + fabsf(rp.z) + fabsf(rp.w);
-        const float k1 = 0.2f * inv_nc * a.loss_scale, k2 = 0.02f * inv_nc * a.loss_scale;
-        auto sgn = [](float x) { return (float)((x > 0.f) - (x < 0.f)); };
-        const float4 dr = make_float4(k1 * ex + k2 * sgn(rp.x), k1 * ey + k2 * sgn(rp.y), k1 * ez + k2 * sgn(rp.z),
-                                      k1 * ew + k2 * sgn(rp.w));
-        const float4 hi = make_float4(tf32_hi(dr.x), tf32_hi(dr.y), tf32_hi(dr.z), tf32_hi(dr.w));
-        float* dp = a.dR + (size_t)row * C + v * 4;
-        *reinterpret_cast<float4*>(dp) = hi;
-        *reinterpret_cast<float4*>(dp + a.plane) = make_float4(dr.x - hi.x, dr.y - hi.y, dr.z - hi.z, dr.w - hi.w);
-      }
+    if (v >= nvec) continue;
+    const float4 p = pred[i], r = raw[i];
+    float4 d;
+    d.x = k_mse * (p.x - r.x) + k_cr * r.x + k_cp * p.x;
+    d.y = k_mse * (p.y - r.y) + k_cr * r.y + k_cp * p.y;
+    d.z = k_mse * (p.z - r.z) + k_cr * r.z + k_cp * p.z;
+    d.w = k_mse * (p.w - r.w) + k_cr * r.w + k_cp * p.w;
+    {
+      const float4 hi = make_float4(tf32_hi(d.x), tf32_hi(d.y), tf32_hi(d.z), tf32_hi(d.w));
+      float* dp = a.dpred + (size_t)row * C + v * 4;
+      *reinterpret_cast<float4*>(dp) = hi;
+      *reinterpret_cast<float4*>(dp + a.plane) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
+    }
+    if (a.gG) {
+      float* dst = a.gG + (size_t)cell * C + v * 4;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+                   : "memory");
+    }
+    if (HAS_R) {
+      // gt_residual = raw - denoised - shared = raw - (pred - R); e = R - gt = pred - raw
+      const float4 q = rp[i];
+      const float ex = p.x - r.x, ey = p.y - r.y, ez = p.z - r.z, ew = p.w - r.w;
+      res_sq += ex * ex + ey * ey + ez * ez + ew * ew;
+      res_abs += fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + fabsf(q.w);
+      const float k1 = 0.2f * inv_nc * a.loss_scale, k2 = 0.02f * inv_nc * a.loss_scale;
+      auto sgn = [](float x) { return (float)((x > 0.f) - (x < 0.f)); };
+      const float4 dr = make_float4(k1 * ex + k2 * sgn(q.x), k1 * ey + k2 * sgn(q.y), k1 * ez + k2 * sgn(q.z),
+                                    k1 * ew + k2 * sgn(q.w));
+      const float4 hi = make_float4(tf32_hi(dr.x), tf32_hi(dr.y), tf32_hi(dr.z), tf32_hi(dr.w));
+      float* dp = a.dR + (size_t)row * C + v * 4;
+      *reinterpret_cast<float4*>(dp) = hi;
+      *reinterpret_cast<float4*>(dp + a.plane) = make_float4(dr.x - hi.x, dr.y - hi.y, dr.z - hi.z, dr.w - hi.w);
     }
   }
-  if (R4) {
+  if (HAS_R) {
     res_sq = warp_sum(res_sq);
     res_abs = warp_sum(res_abs);
   }
+  // loss logging: reduce over the 8 warps of the CTA first -- 2048 warps x 5 atomics on ONE cache line serialise in L2
+  // and used to cost ~20 us of the 25 us this kernel took.
+  __shared__ float s_part[8][5];
+  const int wib = threadIdx.x >> 5;
   if (lane == 0) {
     const float l2 = sse * inv_nc, lc = (1.f - cosv) * inv_n;
     const float lr = 0.1f * res_sq * inv_nc, ls = 0.02f * res_abs * inv_nc;
-    atomicAdd(losses + 0, l2 + lc + lr + ls);
-    atomicAdd(losses + 1, l2);
-    atomicAdd(losses + 2, lc);
-    if (R4) {
-      atomicAdd(losses + 3, lr);
-      atomicAdd(losses + 4, ls);
-    }
+    s_part[wib][0] = l2 + lc + lr + ls;
+    s_part[wib][1] = l2;
+    s_part[wib][2] = lc;
+    s_part[wib][3] = lr;
+    s_part[wib][4] = ls;
   }
+  __syncthreads();
+  if (threadIdx.x < 5 && (HAS_R || threadIdx.x < 3)) {
+    float t = 0.f;
+    const int nw = min(8, a.n - (int)(blockIdx.x * (blockDim.x >> 5)));  // warps of this CTA that own a row
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < nw) t += s_part[k][threadIdx.x];
+    atomicAdd(losses + threadIdx.x, t);
+  }
+}
+
+template <bool HAS_R>
+static int launch_loss_nv(const LossArgs& la, int blocks, int tb, cudaStream_t st) {
+  const int nv = (la.C / 4 + 31) / 32;
+  if (nv <= 1) fit_loss_kernel<1, HAS_R><<<blocks, tb, 0, st>>>(la);
+  else if (nv <= 2) fit_loss_kernel<2, HAS_R><<<blocks, tb, 0, st>>>(la);
+  else if (nv <= 3) fit_loss_kernel<3, HAS_R><<<blocks, tb, 0, st>>>(la);
+  else if (nv <= 6) fit_loss_kernel<6, HAS_R><<<blocks, tb, 0, st>>>(la);
+  else if (nv <= 8) fit_loss_kernel<8, HAS_R><<<blocks, tb, 0, st>>>(la);
+  else fit_loss_kernel<12, HAS_R><<<blocks, tb, 0, st>>>(la);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DVT_OK;
+}
+
+static int launch_loss(const LossArgs& la, cudaStream_t st) {
+  const int tb = 256, blocks = (la.n * 32 + tb - 1) / tb;
+  return la.R ? launch_loss_nv<true>(la, blocks, tb, st) : launch_loss_nv<false>(la, blocks, tb, st);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -400,6 +452,17 @@ fit_adam_table_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __
   // (giving each CTA its own contiguous slice was measured: 133 us instead of 97 us -- channel imbalance)
   const size_t hi = nvec;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // The gradient load depends on the stamp; stamps are therefore fetched one iteration ahead so that the (rare)
+  // gradient loads are issued together with p, m, v instead of one DRAM latency later.
+  uint32_t st_next[ADAM_UNROLL];
+  {
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < ADAM_UNROLL; ++u) {
+      const size_t i = i0 + u * stride;
+      st_next[u] = i < hi ? __ldg(stamp + (i >> 1)) : 0u;
+    }
+  }
   for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += ADAM_UNROLL * stride) {
     float4 pp[ADAM_UNROLL], mm[ADAM_UNROLL], vv[ADAM_UNROLL], gg[ADAM_UNROLL];
     bool ok[ADAM_UNROLL], touched[ADAM_UNROLL];
@@ -407,19 +470,18 @@ fit_adam_table_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __
     for (int u = 0; u < ADAM_UNROLL; ++u) {
       const size_t i = i0 + u * stride;
       ok[u] = i < hi;
-      touched[u] = ok[u] && __ldg(stamp + (i >> 1)) == mark;  // entry = 8 floats = 2 float4
-      if (ok[u]) { pp[u] = p[i]; mm[u] = m[i]; vv[u] = v[i]; }
-    }
-#pragma unroll
-    for (int u = 0; u < ADAM_UNROLL; ++u) {
-      const size_t i = i0 + u * stride;
+      touched[u] = ok[u] && st_next[u] == mark;  // entry = 8 floats = 2 float4
       gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (touched[u]) { gg[u] = g[i]; g[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      if (ok[u]) { pp[u] = p[i]; mm[u] = m[i]; vv[u] = v[i]; }
+      if (touched[u]) gg[u] = g[i];
+      const size_t inext = i + ADAM_UNROLL * stride;
+      st_next[u] = inext < hi ? __ldg(stamp + (inext >> 1)) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < ADAM_UNROLL; ++u) {
       if (!ok[u]) continue;
       const size_t i = i0 + u * stride;
+      if (touched[u]) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       adam1(pp[u].x, mm[u].x, vv[u].x, gg[u].x, wd, s.step_size, s.inv_bc2_sqrt);
       adam1(pp[u].y, mm[u].y, vv[u].y, gg[u].y, wd, s.step_size, s.inv_bc2_sqrt);
       adam1(pp[u].z, mm[u].z, vv[u].z, gg[u].z, wd, s.step_size, s.inv_bc2_sqrt);
@@ -883,27 +945,25 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
     return DVT_OK;
   };
   // ---- forward ----
+  FIT_RC(fork(sB, f->ev[0]));  // side B: gather the sampled bank rows (+ residual MLP forward in phase 2)
+  fit_gather_rows_kernel<<<n, 192, 0, sB>>>(f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
   if (!f->pipeline) FIT_RC(fit_enqueue_encode(f, step_off, /*peek=*/false, st));  // else f->enc is already this step's
   if (phase2) {
-    FIT_RC(fork(sB, f->ev[0]));
-    fit_gather_rows_kernel<<<n, 192, 0, sB>>>(f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw);
-    DVT_CUDA_OK(cudaGetLastError());
-    count_launch();
     FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl));
     FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl));
     FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl));
   }
   FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl));
   FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl));
-  if (phase2) FIT_RC(join(sB, f->ev[1]));
+  FIT_RC(join(sB, f->ev[1]));
   // ---- loss + d pred ----
   LossArgs la;
-  la.bank = f->bank; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
+  la.raw = f->rawb; la.ld_raw = f->ld_raw; la.raw_plane = p_raw; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
   la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.plane = p_nc; la.gG = phase2 ? nullptr : sg + f->G.off;
   la.losses = f->losses; la.n = n; la.C = C; la.hw = f->hw; la.loss_scale = f->loss_scale;
-  fit_loss_kernel<<<(n * 32 + tb - 1) / tb, tb, 0, st>>>(la);
-  DVT_CUDA_OK(cudaGetLastError());
-  count_launch();
+  FIT_RC(launch_loss(la, st));
   // ---- backward ----
   FIT_RC(fork(sB, f->ev[2]));
   if (phase2) FIT_RC(fork(sC, f->ev[3]));

@@ -23,12 +23,13 @@ constexpr int KB_BYTES = 128;  // bytes of K per pipeline stage row (= one 128B 
 // 8 epilogue warps per CTA (two per TMEM lane quadrant, alternating 32-column chunks: twice the ALU throughput and
 // memory-level parallelism of one warp per scheduler).  The x3 (fit) kernels use 128x64 tiles: their problems are small
 // (M = 2048), so narrower tiles mean more CTAs, half the MMA time per k-block and a one-chunk-per-warp epilogue.
-constexpr int epi_warps(bool) { return 8; }
+// The 128x256 bf16 tiles (HP-1) get 12 epilogue warps: their GELU / residual epilogues are ALU- and latency-bound.
+constexpr int epi_warps(int bn, bool x3) { return (bn == 256 && !x3) ? 12 : 8; }
 constexpr int SCR_PITCH = 36;  // floats; 16B-aligned rows, conflict-free for the access pattern below
 
 template <int BN, int STAGES, bool X3 = false>
 struct GemmSmem {
-  static constexpr int EW = epi_warps(X3);
+  static constexpr int EW = epi_warps(BN, X3);
   static constexpr int THREADS = 32 * (2 + EW);
   static constexpr int A_BYTES = BM * KB_BYTES * (X3 ? 2 : 1);  // x3: hi plane then lo plane
   static constexpr int B_BYTES = BN * KB_BYTES * (X3 ? 2 : 1);
@@ -304,8 +305,49 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (m < s.M) xin[jj] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) + (size_t)m * e.ldo + n);
             }
           }
+          const bool plain = e.mask == nullptr && e.mask_f32 == nullptr && e.alpha == 1.0f && has_k;
+          if (plain && e.out_mode == OUT_BF16) {
+            // ---- fast path: bias (+ GELU / ReLU) -> bf16.  The activation is chosen ONCE per chunk, the row loop is
+            // branch-free (QKV and fc1+GELU, the two largest epilogues of the ViT forward).
+            __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
+            if (e.act == ACT_GELU) {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
+              for (int jj = 0; jj < 8; ++jj) {
+                const int m = m0 + 4 * jj;
+                float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+                uint2 pk;
+                pk.x = pack_bf16x2(gelu_erf(x.x + b4.x), gelu_erf(x.y + b4.y));
+                pk.y = pack_bf16x2(gelu_erf(x.z + b4.z), gelu_erf(x.w + b4.w));
+                if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
+              }
+            } else {
+              const float lo = e.act == ACT_RELU ? 0.0f : -INFINITY;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const int m = m0 + 4 * jj;
+                float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+                uint2 pk;
+                pk.x = pack_bf16x2(fmaxf(x.x + b4.x, lo), fmaxf(x.y + b4.y, lo));
+                pk.y = pack_bf16x2(fmaxf(x.z + b4.z, lo), fmaxf(x.w + b4.w, lo));
+                if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
+              }
+            }
+          } else if (plain && e.out_mode == OUT_F32_RESID && e.act == ACT_NONE) {
+            // ---- fast path: x += gamma * (acc + bias)  (attention out-proj, fc2) ----
+            float* outp = reinterpret_cast<float*>(e.out);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int m = m0 + 4 * jj;
+              const float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+              float4 o = xin[jj];
+              o.x = fmaf(g4.x, x.x + b4.x, o.x); o.y = fmaf(g4.y, x.y + b4.y, o.y);
+              o.z = fmaf(g4.z, x.z + b4.z, o.z); o.w = fmaf(g4.w, x.w + b4.w, o.w);
+              if (m < s.M) *reinterpret_cast<float4*>(outp + (size_t)m * e.ldo + n) = o;
+            }
+          } else {
+            // ---- generic path (fit epilogues: masks, split planes, atomics, remap) ----
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
             const int i = (lane >> 3) + 4 * jj;
             const int m = m0 + 4 * jj;
             float4 x = *reinterpret_cast<const float4*>(scr + i * SCR_PITCH + col4);
@@ -335,6 +377,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             } else {
               epi_post4(e, m, n, x);
             }
+          }
           }
         } else {
           // ---------------- ragged N tail: scalar path ----------------

@@ -12,10 +12,11 @@ namespace dvt {
 // Row mapping: input row r = g * in_group + t (t < in_group).  Rows with t < skip are dropped; output row =
 // g * (in_group - skip) + (t - skip).  (skip = number of prefix tokens when writing the patch-only NHWC map.)
 // ----------------------------------------------------------------------------------------------------
-template <typename OutT>
-__global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, OutT* __restrict__ y, int ldy, int rows, int C,
-                                 float eps, int in_group, int skip) {
+// NV = float4 per lane (ceil(C / 128)): the row is loaded with NV independent 16-byte loads per lane before any use.
+template <typename OutT, int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 OutT* __restrict__ y, int ldy, int rows, int C, float eps, int in_group, int skip) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -27,22 +28,21 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
   }
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * ldx);
   const int nvec = C >> 2;
-  float4 v[16];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    v[i] = idx < nvec ? __ldg(xr + idx) : z4;
+  }
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      v[i] = __ldg(xr + idx);
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
+  for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(sum) / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nvec) {
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < nvec) {
       float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       sq += (a * a + b * b) + (c * c + d * d);
     }
@@ -51,7 +51,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int idx = lane + 32 * i;
     if (idx < nvec) {
       const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
@@ -72,6 +72,18 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
   }
 }
 
+template <typename OutT>
+static void launch_ln_nv(int nv, int blocks, int threads, cudaStream_t stream, const float* x, int ldx, const float* gamma,
+                         const float* beta, OutT* y, int ldy, int rows, int C, float eps, int in_group, int skip) {
+#define DVT_LN(NV) layernorm_kernel<OutT, NV><<<blocks, threads, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, C, eps, in_group, skip)
+  if (nv <= 3) DVT_LN(3);
+  else if (nv <= 6) DVT_LN(6);
+  else if (nv <= 8) DVT_LN(8);
+  else if (nv <= 12) DVT_LN(12);
+  else DVT_LN(16);
+#undef DVT_LN
+}
+
 int launch_layernorm(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, bool out_bf16,
                      int rows, int C, float eps, int in_group, int skip, cudaStream_t stream) {
   DVT_REQUIRE(C % 4 == 0 && C <= 2048 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: C=%d ldx=%d ldy=%d unsupported", C,
@@ -79,12 +91,12 @@ int launch_layernorm(const float* x, int ldx, const float* gamma, const float* b
   if (rows <= 0) return DVT_OK;
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
+  const int nv = (C / 4 + 31) / 32;
+  const int grp = in_group > 0 ? in_group : 1;
   if (out_bf16)
-    layernorm_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, rows,
-                                                                     C, eps, in_group > 0 ? in_group : 1, skip);
+    launch_ln_nv<__nv_bfloat16>(nv, blocks, threads, stream, x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, rows, C, eps, grp, skip);
   else
-    layernorm_kernel<float><<<blocks, threads, 0, stream>>>(x, ldx, gamma, beta, (float*)y, ldy, rows, C, eps,
-                                                            in_group > 0 ? in_group : 1, skip);
+    launch_ln_nv<float>(nv, blocks, threads, stream, x, ldx, gamma, beta, (float*)y, ldy, rows, C, eps, grp, skip);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;

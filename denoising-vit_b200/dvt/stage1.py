@@ -38,8 +38,11 @@ class Stage1Pipeline:
         self.h, self.w = (H - P) // S + 1, (W - P) // S + 1
         self.C = vit.n_output_dims
         self.input_size = (H, W)
-        self.field = DVT.NeuralFeatureField(feat_dim=self.C, n_levels=cfg.n_levels)
+        # module parameters live on the GPU: the per-image re-initialisation and the upload into the engine are then
+        # device-side copies (the reference also builds its modules on the GPU, main_img_denoising.py:39-47)
+        self.field = DVT.NeuralFeatureField(feat_dim=self.C, n_levels=cfg.n_levels).cuda()
         self.engine = FitEngine(self.C, self.h, self.w, cfg.pixel_bsz, self.field.meta)
+        self._gen = torch.Generator(device="cuda")
         self._bank: Optional[torch.Tensor] = None
         self._stage: Optional[torch.Tensor] = None
 
@@ -93,17 +96,21 @@ class Stage1Pipeline:
         """bank [V, h, w, C] f32 cuda, coords [V, h, w, 2] in [0,1]; the last view is the un-augmented image.
         Returns denoised_feats [1, h, w, C] (= neural_field(coords[-1]), what the reference saves) and raw [h, w, C]."""
         cfg = self.cfg
-        den = DVT.SingleImageDenoiser(self.h, self.w, self.C, layer_index=self.layer_index)
+        # fresh modules per image, like the reference (new SingleImageDenoiser + NeuralFeatureField for every image)
+        with torch.device("cuda"):
+            den = DVT.SingleImageDenoiser(self.h, self.w, self.C, layer_index=self.layer_index)
         if seed is not None:
-            g = torch.Generator().manual_seed(seed)
-            with torch.no_grad():
-                self.field.neural_field.params.copy_((torch.rand(self.field.meta.n_params, generator=g) * 2 - 1) * 1e-4)
+            self._gen.manual_seed(seed)
+        with torch.no_grad():
+            p = self.field.neural_field.params
+            p.copy_((torch.rand(p.shape, device="cuda", generator=self._gen) * 2 - 1) * 1e-4)  # tcnn-style U(-1e-4, 1e-4)
+            for m in self.field.mlp:
+                if hasattr(m, "reset_parameters"):
+                    m.reset_parameters()
+        self.engine.load_modules(den, self.field)
         if init is not None:
-            self.engine.load_modules(den, self.field)
             for k, v in init.items():
                 self.engine.set_param(k, v)
-        else:
-            self.engine.load_modules(den, self.field)
         V = bank.shape[0]
         self.engine.begin(bank.reshape(V * self.h * self.w, self.C), coords.reshape(-1, 2).to("cuda", torch.float32).contiguous(),
                           idx_stream, lr=cfg.lr, min_lr=cfg.min_lr, warmup_iters=cfg.warmup_iters,
