@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--num-iters", type=int, default=2000)
     ap.add_argument("--warmup-iters", type=int, default=200)
     ap.add_argument("--extract-bsz", type=int, default=16)
-    ap.add_argument("--graph-steps", type=int, default=10)
+    ap.add_argument("--graph-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -220,6 +220,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION/INFO; stdout must carry the one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     V = args.views + 1

@@ -178,13 +178,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         uint32_t sreg[32];
         tmem_ld_32x32(lane_addr + ATT_TM_S + c * 32, sreg);
         tmem_ld_wait();
-        if (partial) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + c * 32 + i < N) m_tile = fmaxf(m_tile, __uint_as_float(sreg[i]));
-        } else {
+        const int nval1 = partial ? N - kbase - c * 32 : 32;  // valid keys in this chunk (warp-uniform)
+        if (nval1 >= 32) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sreg[i]));
+        } else {  // tail chunks of the last key tile only
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nval1) m_tile = fmaxf(m_tile, __uint_as_float(sreg[i]));
         }
       }
       m_tile *= scale_log2e;                      // scale > 0: max commutes with the scaling
@@ -217,16 +218,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           mbar_arrive(s_empty);  // S may now be overwritten by QK of tile j+1
         }
         uint32_t packed[16];
+        const int nval = partial ? N - kbase - c * 32 : 32;  // valid keys in this chunk (warp-uniform)
+        if (nval >= 32) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(sreg[2 * i]), scale_log2e, -m_new));
-          float p1 = ex2(fmaf(__uint_as_float(sreg[2 * i + 1]), scale_log2e, -m_new));
-          if (partial) {
-            if (kbase + c * 32 + 2 * i >= N) p0 = 0.f;
-            if (kbase + c * 32 + 2 * i + 1 >= N) p1 = 0.f;
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2(fmaf(__uint_as_float(sreg[2 * i]), scale_log2e, -m_new));
+            const float p1 = ex2(fmaf(__uint_as_float(sreg[2 * i + 1]), scale_log2e, -m_new));
+            l_tile += p0 + p1;
+            packed[i] = pack_bf16x2(p0, p1);
           }
-          l_tile += p0 + p1;
-          packed[i] = pack_bf16x2(p0, p1);
+        } else {  // tail of the last key tile: keys >= N contribute neither to P nor to the row sum
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = 0.f, p1 = 0.f;
+            if (2 * i < nval) p0 = ex2(fmaf(__uint_as_float(sreg[2 * i]), scale_log2e, -m_new));
+            if (2 * i + 1 < nval) p1 = ex2(fmaf(__uint_as_float(sreg[2 * i + 1]), scale_log2e, -m_new));
+            l_tile += p0 + p1;
+            packed[i] = pack_bf16x2(p0, p1);
+          }
         }
         // keys [c*32, c*32+32) -> k-atom (c >> 1), 16B chunks ((c & 1) * 4 + q), q = 0..3
         uint8_t* atom = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;

@@ -27,7 +27,7 @@ class Stage1Config:
     extract_bsz: int = 32
     pixel_bsz: int = 2048
     loss_scale: float = 1024.0      # torch.amp.GradScaler("cuda", 2**10), never unscaled (main_img_denoising.py:55,88)
-    graph_steps: int = 10
+    graph_steps: int = 20
 
 
 class Stage1Pipeline:
