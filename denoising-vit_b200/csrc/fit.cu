@@ -136,30 +136,50 @@ __global__ void fit_encode_kernel(GridLevels g, const float* __restrict__ table,
   float acc[FIT_F];
 #pragma unroll
   for (int f = 0; f < FIT_F; ++f) acc[f] = 0.f;
+  // all loads of the four corners are issued before the first use (the kernel is pure latency otherwise)
+  float4 pa[4], pb[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const size_t e = c.idx[k];
-    const float4* p = reinterpret_cast<const float4*>(table + e * FIT_F);
-    float4 a = __ldcg(p), b = __ldcg(p + 1);
-    if (pk.enabled) {
+    const float4* p = reinterpret_cast<const float4*>(table + (size_t)c.idx[k] * FIT_F);
+    pa[k] = __ldcg(p);
+    pb[k] = __ldcg(p + 1);
+  }
+  if (pk.enabled) {
+    float4 ma[4], mb[4], va[4], vb[4], ga[4], gb[4];
+    uint32_t stp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t e = c.idx[k];
       const float4* mp = reinterpret_cast<const float4*>(pk.m + e * FIT_F);
       const float4* vp = reinterpret_cast<const float4*>(pk.v + e * FIT_F);
-      float4 ma = __ldcg(mp), mb = __ldcg(mp + 1), va = __ldcg(vp), vb = __ldcg(vp + 1);
-      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
-      if (__ldcg(pk.stamp[par] + e) == (uint32_t)pstep + 1u) {
-        const float4* gp = reinterpret_cast<const float4*>(pk.g[par] + e * FIT_F);
-        ga = __ldcg(gp);
-        gb = __ldcg(gp + 1);
-      }
-      adam1(a.x, ma.x, va.x, ga.x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(a.y, ma.y, va.y, ga.y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(a.z, ma.z, va.z, ga.z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(a.w, ma.w, va.w, ga.w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(b.x, mb.x, vb.x, gb.x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(b.y, mb.y, vb.y, gb.y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(b.z, mb.z, vb.z, gb.z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(b.w, mb.w, vb.w, gb.w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      ma[k] = __ldcg(mp); mb[k] = __ldcg(mp + 1); va[k] = __ldcg(vp); vb[k] = __ldcg(vp + 1);
+      stp[k] = __ldcg(pk.stamp[par] + e);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ga[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gb[k] = ga[k];
+      if (stp[k] == (uint32_t)pstep + 1u) {
+        const float4* gp = reinterpret_cast<const float4*>(pk.g[par] + (size_t)c.idx[k] * FIT_F);
+        ga[k] = __ldcg(gp);
+        gb[k] = __ldcg(gp + 1);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      adam1(pa[k].x, ma[k].x, va[k].x, ga[k].x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(pa[k].y, ma[k].y, va[k].y, ga[k].y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(pa[k].z, ma[k].z, va[k].z, ga[k].z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(pa[k].w, ma[k].w, va[k].w, ga[k].w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(pb[k].x, mb[k].x, vb[k].x, gb[k].x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(pb[k].y, mb[k].y, vb[k].y, gb[k].y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(pb[k].z, mb[k].z, vb[k].z, gb[k].z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+      adam1(pb[k].w, mb[k].w, vb[k].w, gb[k].w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 a = pa[k], b = pb[k];
     acc[0] = fmaf(c.w[k], a.x, acc[0]); acc[1] = fmaf(c.w[k], a.y, acc[1]);
     acc[2] = fmaf(c.w[k], a.z, acc[2]); acc[3] = fmaf(c.w[k], a.w, acc[3]);
     acc[4] = fmaf(c.w[k], b.x, acc[4]); acc[5] = fmaf(c.w[k], b.y, acc[5]);
@@ -438,7 +458,7 @@ static int launch_loss(const LossArgs& la, cudaStream_t st) {
 // (Forcing the maximum shared-memory carve-out on the small kernels was measured as well: it slows this streaming
 // kernel from 97 to 137 us and does not shorten the GEMMs.)
 constexpr int ADAM_UNROLL = 2;
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(1024, 1)
 fit_adam_table_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v, float4* __restrict__ g0,
                       float4* __restrict__ g1, const uint32_t* __restrict__ stamp0, const uint32_t* __restrict__ stamp1,
                       size_t nvec, const AdamScalars* __restrict__ sc, const int* __restrict__ step_base, int step_off,
@@ -890,6 +910,19 @@ static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb
   return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
 }
 
+// Sweep launch geometry.  Default: 8 x #SM CTAs of 256 threads (fastest alone, 77 us).  DVT_FIT_SWEEP_CTAS=n selects n
+// persistent CTAs of 1024 threads, each filling one SM: the remaining SMs stay free for the GEMM chain of the next step
+// when the sweep is software-pipelined (DVT_FIT_PIPELINE=1).
+static void fit_sweep_geometry(int* grid, int* block) {
+  static int ctas = -1;
+  if (ctas < 0) {
+    const char* e = getenv("DVT_FIT_SWEEP_CTAS");
+    ctas = e ? atoi(e) : 0;
+  }
+  if (ctas > 0) { *grid = ctas; *block = 1024; }
+  else { *grid = num_sms() * 8; *block = 256; }
+}
+
 static PeekArgs fit_peek_args(const Fit* f, bool enabled) {
   PeekArgs pk;
   pk.m = f->tm; pk.v = f->tv; pk.g[0] = f->tg[0]; pk.g[1] = f->tg[1];
@@ -995,7 +1028,9 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
         step_off, f->freeze_step, f->wd);
     DVT_CUDA_OK(cudaGetLastError());
     count_launch();
-    fit_adam_table_kernel<<<num_sms() * 8, 256, 0, st>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
+    int sg_ = 0, sb_ = 0;
+    fit_sweep_geometry(&sg_, &sb_);
+    fit_adam_table_kernel<<<sg_, sb_, 0, st>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
                                                           (float4*)f->tg[0], (float4*)f->tg[1], f->tstamp[0],
                                                           f->tstamp[1], f->n_table / 4, f->sc_main, f->step_base, step_off,
                                                           f->wd);
@@ -1019,7 +1054,9 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   FIT_RC(join(sB, f->ev[8]));
   // ---- dense table sweep of this step: forked, joined by the next step (or by fit_sync_sweep) ----
   FIT_RC(fork(sD, f->ev[10]));
-  fit_adam_table_kernel<<<num_sms() * 8, 256, 0, sD>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
+  int sg_ = 0, sb_ = 0;
+  fit_sweep_geometry(&sg_, &sb_);
+  fit_adam_table_kernel<<<sg_, sb_, 0, sD>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
                                                         (float4*)f->tg[0], (float4*)f->tg[1], f->tstamp[0], f->tstamp[1],
                                                         f->n_table / 4, f->sc_main, f->step_base, step_off, f->wd);
   DVT_CUDA_OK(cudaGetLastError());
