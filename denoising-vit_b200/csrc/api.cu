@@ -28,6 +28,7 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t st, int impl);
 int fit_losses(Fit* f, float* dst_host, int num_iters);
 int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, int impl);
 int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, int impl);
+int fit_sweep_once(Fit* f, int ctas, cudaStream_t st);
 int hashgrid_corners(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
                      const uint32_t* hashed, const float* coords, int n, uint32_t* idx, float* w, cudaStream_t st);
 int hashgrid_fwd(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
@@ -261,6 +262,10 @@ int dvt_fit_query(dvt_fit_t* h, const float* coords, int n, float* out, void* st
 int dvt_fit_residual(dvt_fit_t* h, const float* raw, int n, float* out, void* stream) {
   DVT_REQUIRE(h, "dvt_fit_residual: null handle");
   return fit_residual(reinterpret_cast<Fit*>(h), raw, n, out, reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+int dvt_fit_sweep_once(dvt_fit_t* h, int ctas, void* stream) {
+  DVT_REQUIRE(h, "dvt_fit_sweep_once: null handle");
+  return fit_sweep_once(reinterpret_cast<Fit*>(h), ctas, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -72,10 +72,19 @@ __device__ __forceinline__ CornerSet grid_corners(const GridLevels& g, int l, fl
 // The bank rows sampled at step s are idx_all[s * n .. s * n + n).  Inside a captured CUDA graph the step is not
 // a launch-time constant, so kernels take (idx_all, step_base, step_off) and resolve s = *step_base + step_off on
 // the device; idx_all == nullptr means "row i" (query mode).
+// The bank / coordinate pointers of the current fit are read through a device-side record as well (FitInputs), so a
+// captured graph stays valid when the next image's bank lives in another buffer.
+struct FitInputs {
+  const float* bank;
+  const float* coords;
+};
 struct StepRows {
   const int* idx_all;
   const int* step_base;
   int step_off;
+  const FitInputs* in;  // nullptr: the kernel's direct bank / coords argument is used (query mode, unit tests)
+  __device__ __forceinline__ const float* coords(const float* direct) const { return in ? in->coords : direct; }
+  __device__ __forceinline__ const float* bank(const float* direct) const { return in ? in->bank : direct; }
   __device__ __forceinline__ int step() const { return *step_base + step_off; }
   __device__ __forceinline__ const int* rows(int n) const {
     return idx_all ? idx_all + (size_t)step() * n : nullptr;
@@ -106,96 +115,98 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
   p = fmaf(-ss, __fdividef(m, denom), p);
 }
 
-struct PeekArgs {       // all null / 0 when the table is up to date
-  const float* m;       // Adam moments of the table
-  const float* v;
-  const float* g[2];    // gradient buffers by step parity
-  const uint32_t* stamp[2];
-  const AdamScalars* sc;
-  float wd;
-  int enabled;
+// Optimiser state of the hash table.  State S_t (after t Adam steps) lives in p/m/v[t & 1]: the dense sweep of step t
+// reads buffer t & 1 and writes the other one, so S_t stays readable while the sweep runs.  The gradient of step t is
+// accumulated into g[t % 3]; stamp[t % 3][entry] == t + 1 marks the entries it touched.
+struct TableBufs {
+  float* p[2];
+  float* m[2];
+  float* v[2];
+  float* g[3];
+  uint32_t* stamp[3];
 };
+__device__ __forceinline__ int mod3(int x) { return x % 3; }
+#define DVT_SEL2(arr, i) ((i) ? (arr)[1] : (arr)[0])
+#define DVT_SEL3(arr, i) ((i) == 0 ? (arr)[0] : ((i) == 1 ? (arr)[1] : (arr)[2]))
 
-__global__ void fit_encode_kernel(GridLevels g, const float* __restrict__ table, const float* __restrict__ coords,
-                                  StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane, PeekArgs pk) {
+__device__ __forceinline__ void adam8(float4& pa, float4& pb, float4& ma, float4& mb, float4& va, float4& vb,
+                                      const float4& ga, const float4& gb, float wd, const AdamScalars s) {
+  adam1(pa.x, ma.x, va.x, ga.x, wd, s.step_size, s.inv_bc2_sqrt);
+  adam1(pa.y, ma.y, va.y, ga.y, wd, s.step_size, s.inv_bc2_sqrt);
+  adam1(pa.z, ma.z, va.z, ga.z, wd, s.step_size, s.inv_bc2_sqrt);
+  adam1(pa.w, ma.w, va.w, ga.w, wd, s.step_size, s.inv_bc2_sqrt);
+  adam1(pb.x, mb.x, vb.x, gb.x, wd, s.step_size, s.inv_bc2_sqrt);
+  adam1(pb.y, mb.y, vb.y, gb.y, wd, s.step_size, s.inv_bc2_sqrt);
+  adam1(pb.z, mb.z, vb.z, gb.z, wd, s.step_size, s.inv_bc2_sqrt);
+  adam1(pb.w, mb.w, vb.w, gb.w, wd, s.step_size, s.inv_bc2_sqrt);
+}
+
+// One thread per (sample, level, corner); the four corners of a cell sit in adjacent lanes and are combined with two
+// shuffles.  npeek = number of Adam steps (0, 1 or 2) that are still pending in the sweeps and are applied on the fly:
+// the encoded step is s, the state that is read is S_{s - npeek}.  table_fixed != nullptr: read that table (query mode).
+__global__ void __launch_bounds__(256)
+fit_encode_kernel(GridLevels g, TableBufs tb, const float* __restrict__ table_fixed, const float* __restrict__ coords,
+                  StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane,
+                  const AdamScalars* __restrict__ sc, float wd, int npeek) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * g.n_levels) return;
-  const int i = t % n, l = t / n;
+  const int q = t >> 2, k = t & 3;
+  if (q >= n * g.n_levels) return;  // n % 8 == 0: warps are either complete or empty
+  const int i = q % n, l = q / n;
   const int* rows = sr.rows(n);
   const int r = rows ? rows[i] : i;
-  const float2 xy = *reinterpret_cast<const float2*>(coords + 2 * (size_t)r);
-  const CornerSet c = grid_corners(g, l, xy.x, xy.y);
-  // pending Adam step = (step being encoded) - 1
-  int pstep = 0, par = 0;
-  AdamScalars ps{0.f, 1.f};
-  if (pk.enabled) {
-    pstep = sr.step() - 1;
-    par = pstep & 1;
-    ps = pk.sc[pstep];
-  }
-  float acc[FIT_F];
-#pragma unroll
-  for (int f = 0; f < FIT_F; ++f) acc[f] = 0.f;
-  // all loads of the four corners are issued before the first use (the kernel is pure latency otherwise)
-  float4 pa[4], pb[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float4* p = reinterpret_cast<const float4*>(table + (size_t)c.idx[k] * FIT_F);
-    pa[k] = __ldcg(p);
-    pb[k] = __ldcg(p + 1);
-  }
-  if (pk.enabled) {
-    float4 ma[4], mb[4], va[4], vb[4], ga[4], gb[4];
-    uint32_t stp[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t e = c.idx[k];
-      const float4* mp = reinterpret_cast<const float4*>(pk.m + e * FIT_F);
-      const float4* vp = reinterpret_cast<const float4*>(pk.v + e * FIT_F);
-      ma[k] = __ldcg(mp); mb[k] = __ldcg(mp + 1); va[k] = __ldcg(vp); vb[k] = __ldcg(vp + 1);
-      stp[k] = __ldcg(pk.stamp[par] + e);
+  const float2 xy = *reinterpret_cast<const float2*>(sr.coords(coords) + 2 * (size_t)r);
+  // corner k of the cell (same arithmetic as grid_corners)
+  const float s = g.scale[l];
+  float px = fmaf(s, xy.x, 0.5f), py = fmaf(s, xy.y, 0.5f);
+  const float fx = floorf(px), fy = floorf(py);
+  const uint32_t cx = (uint32_t)(int)fx, cy = (uint32_t)(int)fy;
+  px -= fx;
+  py -= fy;
+  const int dx = k & 1, dy = k >> 1;
+  const size_t e = g.offset[l] + grid_index(g, l, cx + dx, cy + dy);
+  const float w = (dx ? px : 1.f - px) * (dy ? py : 1.f - py);
+  const int b = table_fixed ? 0 : sr.step() - npeek;  // state that is read
+  const float* P = table_fixed ? table_fixed : DVT_SEL2(tb.p, b & 1);
+  float4 pa = __ldcg(reinterpret_cast<const float4*>(P + e * FIT_F));
+  float4 pb = __ldcg(reinterpret_cast<const float4*>(P + e * FIT_F) + 1);
+  if (npeek > 0) {
+    const float4* mp = reinterpret_cast<const float4*>(DVT_SEL2(tb.m, b & 1) + e * FIT_F);
+    const float4* vp = reinterpret_cast<const float4*>(DVT_SEL2(tb.v, b & 1) + e * FIT_F);
+    float4 ma = __ldcg(mp), mb = __ldcg(mp + 1), va = __ldcg(vp), vb = __ldcg(vp + 1);
+    const int r0 = mod3(b), r1 = mod3(b + 1);
+    const uint32_t s0 = __ldcg(DVT_SEL3(tb.stamp, r0) + e);
+    const uint32_t s1 = npeek > 1 ? __ldcg(DVT_SEL3(tb.stamp, r1) + e) : 0u;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g0a = z4, g0b = z4, g1a = z4, g1b = z4;
+    if (s0 == (uint32_t)b + 1u) {
+      const float4* gp = reinterpret_cast<const float4*>(DVT_SEL3(tb.g, r0) + e * FIT_F);
+      g0a = __ldcg(gp);
+      g0b = __ldcg(gp + 1);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      ga[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      gb[k] = ga[k];
-      if (stp[k] == (uint32_t)pstep + 1u) {
-        const float4* gp = reinterpret_cast<const float4*>(pk.g[par] + (size_t)c.idx[k] * FIT_F);
-        ga[k] = __ldcg(gp);
-        gb[k] = __ldcg(gp + 1);
-      }
+    if (npeek > 1 && s1 == (uint32_t)b + 2u) {
+      const float4* gp = reinterpret_cast<const float4*>(DVT_SEL3(tb.g, r1) + e * FIT_F);
+      g1a = __ldcg(gp);
+      g1b = __ldcg(gp + 1);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      adam1(pa[k].x, ma[k].x, va[k].x, ga[k].x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(pa[k].y, ma[k].y, va[k].y, ga[k].y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(pa[k].z, ma[k].z, va[k].z, ga[k].z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(pa[k].w, ma[k].w, va[k].w, ga[k].w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(pb[k].x, mb[k].x, vb[k].x, gb[k].x, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(pb[k].y, mb[k].y, vb[k].y, gb[k].y, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(pb[k].z, mb[k].z, vb[k].z, gb[k].z, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-      adam1(pb[k].w, mb[k].w, vb[k].w, gb[k].w, pk.wd, ps.step_size, ps.inv_bc2_sqrt);
-    }
+    adam8(pa, pb, ma, mb, va, vb, g0a, g0b, wd, sc[b]);
+    if (npeek > 1) adam8(pa, pb, ma, mb, va, vb, g1a, g1b, wd, sc[b + 1]);
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float4 a = pa[k], b = pb[k];
-    acc[0] = fmaf(c.w[k], a.x, acc[0]); acc[1] = fmaf(c.w[k], a.y, acc[1]);
-    acc[2] = fmaf(c.w[k], a.z, acc[2]); acc[3] = fmaf(c.w[k], a.w, acc[3]);
-    acc[4] = fmaf(c.w[k], b.x, acc[4]); acc[5] = fmaf(c.w[k], b.y, acc[5]);
-    acc[6] = fmaf(c.w[k], b.z, acc[6]); acc[7] = fmaf(c.w[k], b.w, acc[7]);
-  }
-  float hi[FIT_F], lo[FIT_F];
+  float acc[FIT_F] = {w * pa.x, w * pa.y, w * pa.z, w * pa.w, w * pb.x, w * pb.y, w * pb.z, w * pb.w};
 #pragma unroll
   for (int f = 0; f < FIT_F; ++f) {
-    hi[f] = tf32_hi(acc[f]);
-    lo[f] = acc[f] - hi[f];
+    acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 1);
+    acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 2);
   }
-  float* dst = enc + (size_t)i * ld_enc + l * FIT_F;
-  *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-  *reinterpret_cast<float4*>(dst + plane) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-  *reinterpret_cast<float4*>(dst + plane + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+  // lane k stores one float4: k = 0/1 the hi plane (features 0-3 / 4-7), k = 2/3 the lo plane
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = (k & 1) ? acc[4 + j] : acc[j];
+    const float hi = tf32_hi(a);
+    o[j] = (k & 2) ? a - hi : hi;
+  }
+  float* dst = enc + (size_t)i * ld_enc + l * FIT_F + (k & 1) * 4 + ((k & 2) ? plane : 0);
+  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // fp32 encode (unit-test entry point: bit-level check of indices / weights against the oracle)
@@ -229,28 +240,28 @@ __global__ void fit_corners_kernel(GridLevels g, const float* __restrict__ coord
 // backward of the encoding: dense-table gradient accumulation with vector atomics
 // `stamp` (optional): stamp[entry] = step + 1 marks the entries that received a gradient this step, so that the dense
 // Adam sweep reads (and re-zeroes) the gradient of touched entries only: 24 B/param of traffic instead of 32.
-// Two gradient / stamp buffers alternate by step parity: the sweep of step t consumes (and re-zeroes) buffer t & 1
-// while the backward of step t+1 already accumulates into the other one.
+// The gradient / stamp buffers form a ring of three (TableBufs): the backward of step t writes ring slot t % 3 while the
+// sweeps of steps t-1 / t-2 may still be reading theirs.  tb.stamp[0] == nullptr: plain accumulation into tb.g[0]
+// (unit-test entry point).
 __global__ void fit_grid_bwd_kernel(GridLevels g, const float* __restrict__ coords, StepRows sr, int n,
-                                    const float* __restrict__ denc, int ld_denc, float* __restrict__ gtable0,
-                                    float* __restrict__ gtable1, uint32_t* __restrict__ stamp0,
-                                    uint32_t* __restrict__ stamp1) {
+                                    const float* __restrict__ denc, int ld_denc, TableBufs tb) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * g.n_levels) return;
   const int i = t % n, l = t / n;
   const int* rows = sr.rows(n);
   const int r = rows ? rows[i] : i;
-  const float2 xy = *reinterpret_cast<const float2*>(coords + 2 * (size_t)r);
+  const float2 xy = *reinterpret_cast<const float2*>(sr.coords(coords) + 2 * (size_t)r);
   const CornerSet c = grid_corners(g, l, xy.x, xy.y);
   const float4 a = *reinterpret_cast<const float4*>(denc + (size_t)i * ld_denc + l * FIT_F);
   const float4 b = *reinterpret_cast<const float4*>(denc + (size_t)i * ld_denc + l * FIT_F + 4);
-  const int par = stamp0 ? (sr.step() & 1) : 0;
-  float* gtable = par ? gtable1 : gtable0;
-  uint32_t* stamp = par ? stamp1 : stamp0;
-  const uint32_t mark = stamp ? (uint32_t)sr.step() + 1u : 0u;
+  const bool stamped = tb.stamp[0] != nullptr;
+  const int slot = stamped ? mod3(sr.step()) : 0;
+  float* gtable = DVT_SEL3(tb.g, slot);
+  uint32_t* stamp = DVT_SEL3(tb.stamp, slot);
+  const uint32_t mark = stamped ? (uint32_t)sr.step() + 1u : 0u;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (stamp) stamp[c.idx[k]] = mark;
+    if (stamped) stamp[c.idx[k]] = mark;
     float* dst = gtable + (size_t)c.idx[k] * FIT_F;
     const float w = c.w[k];
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w * a.x), "f"(w * a.y), "f"(w * a.z),
@@ -267,7 +278,7 @@ __global__ void fit_gather_rows_kernel(const float* __restrict__ bank, int C, St
                                        float* __restrict__ out, int ld, size_t plane) {
   const int i = blockIdx.x;
   const int* rows = sr.rows(n);
-  const float4* src = reinterpret_cast<const float4*>(bank + (size_t)(rows ? rows[i] : i) * C);
+  const float4* src = reinterpret_cast<const float4*>(sr.bank(bank) + (size_t)(rows ? rows[i] : i) * C);
   for (int c4 = threadIdx.x; c4 < C / 4; c4 += blockDim.x) {
     const float4 v = __ldg(src + c4);
     const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
@@ -452,61 +463,74 @@ static int launch_loss(const LossArgs& la, cudaStream_t st) {
 // ----------------------------------------------------------------------------------------------------
 // (AdamScalars / adam1() are defined above, next to the encode kernel that also applies them.)
 
-// Many short-lived CTAs (8 per SM, <= 64 registers): the sweep of step t runs on a LOW-priority stream beside the GEMM
-// chain of step t+1; when a sweep CTA retires, the block scheduler hands its slot to a waiting high-priority chain CTA.
-// (A persistent one-CTA-per-SM sweep was measured too: it cannot keep enough loads in flight to saturate HBM.)
-// (Forcing the maximum shared-memory carve-out on the small kernels was measured as well: it slows this streaming
-// kernel from 97 to 137 us and does not shorten the GEMMs.)
+// Dense sweep of step t: S_{t+1} = Adam(S_t, g_t), read from state buffer t & 1, written to the other one (24 B/param +
+// stamps).  Gradients are read for stamped entries only.  The gradient slot of step t-1 is re-zeroed here (not its own:
+// the encode kernel may still be "peeking" at g_t while this sweep runs); the backward of step t+2, which reuses that
+// slot, is ordered after this sweep by the host.
+// Launch geometries (fit_sweep_geometry): many short-lived 256-thread CTAs (fastest alone: 77 us, the HBM peak), or a
+// few persistent 1024-thread CTAs that fill one SM each and leave the other SMs to the GEMM chain of the next steps.
+// (Measured and rejected: one contiguous slice per CTA -- 133 us, HBM channel imbalance; maximum shared-memory
+// carve-out -- 137 us.)
 constexpr int ADAM_UNROLL = 2;
 __global__ void __launch_bounds__(1024, 1)
-fit_adam_table_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v, float4* __restrict__ g0,
-                      float4* __restrict__ g1, const uint32_t* __restrict__ stamp0, const uint32_t* __restrict__ stamp1,
-                      size_t nvec, const AdamScalars* __restrict__ sc, const int* __restrict__ step_base, int step_off,
-                      float wd) {
+fit_adam_table_kernel(TableBufs tb, size_t nvec, const AdamScalars* __restrict__ sc, const int* __restrict__ step_base,
+                      int step_off, float wd) {
   const int step = *step_base + step_off;
-  float4* __restrict__ g = (step & 1) ? g1 : g0;
-  const uint32_t* __restrict__ stamp = (step & 1) ? stamp1 : stamp0;
+  const int src = step & 1, slot = mod3(step), slot_prev = mod3(step + 2);
+  const float4* __restrict__ p = reinterpret_cast<const float4*>(DVT_SEL2(tb.p, src));
+  const float4* __restrict__ m = reinterpret_cast<const float4*>(DVT_SEL2(tb.m, src));
+  const float4* __restrict__ v = reinterpret_cast<const float4*>(DVT_SEL2(tb.v, src));
+  float4* __restrict__ po = reinterpret_cast<float4*>(DVT_SEL2(tb.p, src ^ 1));
+  float4* __restrict__ mo = reinterpret_cast<float4*>(DVT_SEL2(tb.m, src ^ 1));
+  float4* __restrict__ vo = reinterpret_cast<float4*>(DVT_SEL2(tb.v, src ^ 1));
+  const float4* __restrict__ g = reinterpret_cast<const float4*>(DVT_SEL3(tb.g, slot));
+  const uint32_t* __restrict__ stamp = DVT_SEL3(tb.stamp, slot);
+  float4* __restrict__ gz = reinterpret_cast<float4*>(DVT_SEL3(tb.g, slot_prev));
+  const uint32_t* __restrict__ stamp_z = DVT_SEL3(tb.stamp, slot_prev);
   const AdamScalars s = sc[step];
   const uint32_t mark = (uint32_t)step + 1u;
+  const uint32_t mark_z = step > 0 ? (uint32_t)step : 0xffffffffu;  // stamp of step - 1 (never matches at step 0)
   // grid-stride: all CTAs advance one contiguous front together, which spreads the traffic evenly over the HBM channels
-  // (giving each CTA its own contiguous slice was measured: 133 us instead of 97 us -- channel imbalance)
   const size_t hi = nvec;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   // The gradient load depends on the stamp; stamps are therefore fetched one iteration ahead so that the (rare)
   // gradient loads are issued together with p, m, v instead of one DRAM latency later.
-  uint32_t st_next[ADAM_UNROLL];
+  uint32_t st_next[ADAM_UNROLL], sz_next[ADAM_UNROLL];
   {
     const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int u = 0; u < ADAM_UNROLL; ++u) {
       const size_t i = i0 + u * stride;
       st_next[u] = i < hi ? __ldg(stamp + (i >> 1)) : 0u;
+      sz_next[u] = i < hi ? __ldg(stamp_z + (i >> 1)) : 0u;
     }
   }
   for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += ADAM_UNROLL * stride) {
     float4 pp[ADAM_UNROLL], mm[ADAM_UNROLL], vv[ADAM_UNROLL], gg[ADAM_UNROLL];
-    bool ok[ADAM_UNROLL], touched[ADAM_UNROLL];
+    bool ok[ADAM_UNROLL];
 #pragma unroll
     for (int u = 0; u < ADAM_UNROLL; ++u) {
       const size_t i = i0 + u * stride;
       ok[u] = i < hi;
-      touched[u] = ok[u] && st_next[u] == mark;  // entry = 8 floats = 2 float4
+      const bool touched = ok[u] && st_next[u] == mark;  // entry = 8 floats = 2 float4
+      const bool stale = ok[u] && sz_next[u] == mark_z;
       gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok[u]) { pp[u] = p[i]; mm[u] = m[i]; vv[u] = v[i]; }
-      if (touched[u]) gg[u] = g[i];
+      if (touched) gg[u] = g[i];
+      if (stale) gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const size_t inext = i + ADAM_UNROLL * stride;
       st_next[u] = inext < hi ? __ldg(stamp + (inext >> 1)) : 0u;
+      sz_next[u] = inext < hi ? __ldg(stamp_z + (inext >> 1)) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < ADAM_UNROLL; ++u) {
       if (!ok[u]) continue;
       const size_t i = i0 + u * stride;
-      if (touched[u]) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       adam1(pp[u].x, mm[u].x, vv[u].x, gg[u].x, wd, s.step_size, s.inv_bc2_sqrt);
       adam1(pp[u].y, mm[u].y, vv[u].y, gg[u].y, wd, s.step_size, s.inv_bc2_sqrt);
       adam1(pp[u].z, mm[u].z, vv[u].z, gg[u].z, wd, s.step_size, s.inv_bc2_sqrt);
       adam1(pp[u].w, mm[u].w, vv[u].w, gg[u].w, wd, s.step_size, s.inv_bc2_sqrt);
-      p[i] = pp[u]; m[i] = mm[u]; v[i] = vv[u];
+      po[i] = pp[u]; mo[i] = mm[u]; vo[i] = vv[u];
     }
   }
 }
@@ -587,13 +611,14 @@ struct Fit {
   Seg W1, b1, W2, b2, G, R1, rb1, R2, rb2, R3, rb3;
   int n_small = 0;
   // device memory
-  float *tp = nullptr, *tm = nullptr, *tv = nullptr;
-  float* tg[2] = {nullptr, nullptr};          // dense gradient of the table, by step parity
-  uint32_t* tstamp[2] = {nullptr, nullptr};   // [n_entries] step + 1 of the last gradient written, by step parity
-  cudaStream_t sD = nullptr;                   // stream of the pipelined table sweep
-  bool sweep_pending = false;                  // a sweep has been enqueued on sD and not yet joined
+  TableBufs tb = {};                           // ping-pong p/m/v, ring of three gradient / stamp buffers
+  int cur_host = 0;                            // steps completed (host view): the current table is tb.p[cur_host & 1]
+  cudaStream_t sD = nullptr;                   // stream of the pipelined table sweeps
+  cudaEvent_t ev_sweep[3] = {};                // completion of the sweep launched at epoch step i (slot i % 3)
+  int epoch_steps = 0;                         // pipelined steps enqueued since the sweeps were last joined
   bool enc_ready = false;                      // f->enc already holds the encoding of the next step
-  bool pipeline = false;                       // software-pipelined table sweep (see fit_enqueue_step)
+  bool pipe[2] = {true, true};                 // software-pipelined table sweep in phase 1 / 2 (see fit_enqueue_step)
+  int sweep_ctas[2] = {0, 0};                  // persistent sweep CTAs in phase 1 / 2 (0 = many small CTAs)
   float *sp = nullptr, *sm = nullptr, *sv = nullptr, *sg = nullptr;
   float* wsplit = nullptr;  // [2][n_small] TF32 hi / lo planes of the small params (x3 GEMM operands)
   // activations: GEMM operands are stored as two fp32 planes (hi, lo), plane stride = bsz * ld
@@ -613,6 +638,7 @@ struct Fit {
   const float* bank = nullptr;
   const float* coords = nullptr;
   size_t bank_rows = 0;
+  FitInputs* inputs_dev = nullptr;  // device copy of {bank, coords}: what the (graph-captured) kernels dereference
   // graphs (captured on a stream owned by the engine: the caller's stream may be the legacy default stream,
   // which cannot be captured)
   cudaGraphExec_t graph1 = nullptr, graph2 = nullptr;
@@ -657,11 +683,26 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sC, cudaStreamNonBlocking, prio_hi));
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sD, cudaStreamNonBlocking, prio_lo));  // the sweep yields to the chain
   for (auto& e : f->ev) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : f->ev_sweep) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
   DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_out, cudaEventDisableTiming));
   {
+    // Schedule knobs (defaults = the fastest measured at the headline size, profiles/r1w_fit_schedules.txt):
+    //   DVT_FIT_SWEEP_CTAS="a[,b]"  per phase (1 [, 2]): n > 0 pipelined sweep on n persistent CTAs (1024 threads, one
+    //                               per SM); 0 pipelined sweep on 8 x #SM CTAs of 256 threads; -1 sequential schedule
+    //   DVT_FIT_PIPELINE=0          sequential schedule in both phases
+    int cfg[2] = {40, -1};
+    if (const char* se = getenv("DVT_FIT_SWEEP_CTAS")) {
+      int a = 0, b = 0;
+      const int got = sscanf(se, "%d,%d", &a, &b);
+      if (got >= 1) { cfg[0] = a; cfg[1] = got >= 2 ? b : a; }
+    }
     const char* pe = getenv("DVT_FIT_PIPELINE");
-    f->pipeline = pe && pe[0] == '1';
+    const bool off = pe && pe[0] == '0';
+    for (int q = 0; q < 2; ++q) {
+      f->pipe[q] = !off && cfg[q] >= 0;
+      f->sweep_ctas[q] = f->pipe[q] ? std::min(cfg[q], num_sms()) : 0;
+    }
   }
   f->C = C; f->gh = gh; f->gw = gw; f->hw = gh * gw; f->bsz = bsz; f->Lf = n_levels * FIT_F;
   f->grid.n_levels = n_levels;
@@ -681,9 +722,12 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   f->ld_enc = f->Lf + 8; f->ld_h1 = H1 + 8; f->ld_raw = C + 8; f->ld_r = Hr + 8;
   int rc = 0;
   auto A = [&](void** p, size_t bytes) { if (!rc) rc = fit_alloc(f, p, bytes); };
-  A((void**)&f->tp, f->n_table * 4); A((void**)&f->tm, f->n_table * 4); A((void**)&f->tv, f->n_table * 4);
-  A((void**)&f->tg[0], f->n_table * 4); A((void**)&f->tg[1], f->n_table * 4);
-  A((void**)&f->tstamp[0], f->n_table / FIT_F * 4); A((void**)&f->tstamp[1], f->n_table / FIT_F * 4);
+  for (int q = 0; q < 2; ++q) {
+    A((void**)&f->tb.p[q], f->n_table * 4); A((void**)&f->tb.m[q], f->n_table * 4); A((void**)&f->tb.v[q], f->n_table * 4);
+  }
+  for (int q = 0; q < 3; ++q) {
+    A((void**)&f->tb.g[q], f->n_table * 4); A((void**)&f->tb.stamp[q], f->n_table / FIT_F * 4);
+  }
   A((void**)&f->sp, (size_t)off * 4); A((void**)&f->sm, (size_t)off * 4); A((void**)&f->sv, (size_t)off * 4);
   A((void**)&f->sg, (size_t)off * 4); A((void**)&f->wsplit, (size_t)off * 8);
   const size_t n = bsz;
@@ -692,6 +736,7 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   A((void**)&f->rawb, n * f->ld_raw * 8); A((void**)&f->r1, n * f->ld_r * 8); A((void**)&f->r2, n * f->ld_r * 8);
   A((void**)&f->dR, n * C * 8); A((void**)&f->dr2, n * Hr * 8); A((void**)&f->dr1, n * Hr * 8);
   A((void**)&f->Rout, n * C * 4); A((void**)&f->step_base, sizeof(int));
+  A((void**)&f->inputs_dev, sizeof(FitInputs));
   if (rc) { for (void* p : f->owned) cudaFree(p); delete f; return rc; }
   // ones columns (bias gradients through the weight-gradient GEMMs)
   const int tb = 256, nb = (bsz + tb - 1) / tb;
@@ -719,6 +764,7 @@ void fit_destroy(Fit* f) {
   if (f->sC) cudaStreamDestroy(f->sC);
   if (f->sD) cudaStreamDestroy(f->sD);
   for (auto& e : f->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : f->ev_sweep) if (e) cudaEventDestroy(e);
   if (f->ev_in) cudaEventDestroy(f->ev_in);
   if (f->ev_out) cudaEventDestroy(f->ev_out);
   for (void* p : f->owned) cudaFree(p);
@@ -751,7 +797,8 @@ int fit_set_param(Fit* f, const char* name_c, const float* src, size_t numel) {
   const std::string name(name_c);
   if (name == "table") {
     DVT_REQUIRE(numel == f->n_table, "fit_set_param: table has %zu elements, expected %zu", numel, f->n_table);
-    DVT_CUDA_OK(cudaMemcpy(f->tp, src, numel * 4, cudaMemcpyDefault));
+    DVT_CUDA_OK(cudaDeviceSynchronize());
+    DVT_CUDA_OK(cudaMemcpy(f->tb.p[f->cur_host & 1], src, numel * 4, cudaMemcpyDefault));
     return DVT_OK;
   }
   Seg* s = nullptr;
@@ -776,7 +823,7 @@ int fit_get_param(Fit* f, const char* name_c, float* dst, size_t numel) {
   DVT_CUDA_OK(cudaDeviceSynchronize());
   if (name == "table") {
     DVT_REQUIRE(numel == f->n_table, "fit_get_param: table size mismatch");
-    DVT_CUDA_OK(cudaMemcpy(dst, f->tp, numel * 4, cudaMemcpyDefault));
+    DVT_CUDA_OK(cudaMemcpy(dst, f->tb.p[f->cur_host & 1], numel * 4, cudaMemcpyDefault));
     return DVT_OK;
   }
   Seg* s = nullptr;
@@ -801,6 +848,12 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   DVT_REQUIRE(bank && coords && idx_host && num_iters > 0, "fit_begin: bad arguments");
   DVT_REQUIRE(bank_rows % (size_t)f->hw == 0, "fit_begin: bank rows %zu not a multiple of h*w = %d", bank_rows, f->hw);
   f->bank = bank; f->coords = coords; f->bank_rows = bank_rows;
+  {
+    const FitInputs in{bank, coords};
+    DVT_CUDA_OK(cudaMemcpy(f->inputs_dev, &in, sizeof(in), cudaMemcpyHostToDevice));
+  }
+  // scalars that are baked into captured kernel nodes
+  if (f->wd != weight_decay || f->loss_scale != loss_scale) fit_drop_graphs(f);
   f->wd = weight_decay; f->loss_scale = loss_scale;
   // coordinates must lie in [0, 1] (assert of neural_feature_field.py:47, checked once per bank instead of per step)
   int* bad = nullptr;
@@ -851,13 +904,17 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   DVT_CUDA_OK(cudaMemcpy(f->sc_res, b.data(), b.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
   DVT_CUDA_OK(cudaMemset(f->losses, 0, (size_t)num_iters * 5 * 4));
   DVT_CUDA_OK(cudaMemset(f->step_base, 0, 4));
-  DVT_CUDA_OK(cudaMemset(f->tm, 0, f->n_table * 4)); DVT_CUDA_OK(cudaMemset(f->tv, 0, f->n_table * 4));
-  for (int q = 0; q < 2; ++q) {
-    DVT_CUDA_OK(cudaMemset(f->tg[q], 0, f->n_table * 4));
-    DVT_CUDA_OK(cudaMemset(f->tstamp[q], 0, f->n_table / FIT_F * 4));
+  DVT_CUDA_OK(cudaDeviceSynchronize());
+  if (f->cur_host & 1)  // the schedule restarts at step 0, whose state lives in buffer 0
+    DVT_CUDA_OK(cudaMemcpy(f->tb.p[0], f->tb.p[1], f->n_table * 4, cudaMemcpyDeviceToDevice));
+  f->cur_host = 0;
+  DVT_CUDA_OK(cudaMemset(f->tb.m[0], 0, f->n_table * 4)); DVT_CUDA_OK(cudaMemset(f->tb.v[0], 0, f->n_table * 4));
+  for (int q = 0; q < 3; ++q) {
+    DVT_CUDA_OK(cudaMemset(f->tb.g[q], 0, f->n_table * 4));
+    DVT_CUDA_OK(cudaMemset(f->tb.stamp[q], 0, f->n_table / FIT_F * 4));
   }
   f->enc_ready = false;
-  f->sweep_pending = false;
+  f->epoch_steps = 0;
   DVT_CUDA_OK(cudaMemset(f->sm, 0, (size_t)f->n_small * 4)); DVT_CUDA_OK(cudaMemset(f->sv, 0, (size_t)f->n_small * 4));
   DVT_CUDA_OK(cudaMemset(f->sg, 0, (size_t)f->n_small * 4));
   fit_split_kernel<<<256, 256>>>(f->sp, f->wsplit, (size_t)f->n_small);
@@ -910,52 +967,51 @@ static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb
   return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
 }
 
-// Sweep launch geometry.  Default: 8 x #SM CTAs of 256 threads (fastest alone, 77 us).  DVT_FIT_SWEEP_CTAS=n selects n
-// persistent CTAs of 1024 threads, each filling one SM: the remaining SMs stay free for the GEMM chain of the next step
-// when the sweep is software-pipelined (DVT_FIT_PIPELINE=1).
-static void fit_sweep_geometry(int* grid, int* block) {
-  static int ctas = -1;
-  if (ctas < 0) {
-    const char* e = getenv("DVT_FIT_SWEEP_CTAS");
-    ctas = e ? atoi(e) : 0;
-  }
+// Sweep launch geometry: n > 0 persistent CTAs of 1024 threads (one per SM: the register file is full, so the GEMM
+// chain of the next steps keeps the other SMs), else 8 x #SM CTAs of 256 threads (fastest when running alone).
+static void fit_sweep_geometry(const Fit* f, bool phase2, int* grid, int* block) {
+  const int ctas = f->sweep_ctas[phase2 ? 1 : 0];
   if (ctas > 0) { *grid = ctas; *block = 1024; }
   else { *grid = num_sms() * 8; *block = 256; }
 }
 
-static PeekArgs fit_peek_args(const Fit* f, bool enabled) {
-  PeekArgs pk;
-  pk.m = f->tm; pk.v = f->tv; pk.g[0] = f->tg[0]; pk.g[1] = f->tg[1];
-  pk.stamp[0] = f->tstamp[0]; pk.stamp[1] = f->tstamp[1];
-  pk.sc = f->sc_main; pk.wd = f->wd; pk.enabled = enabled ? 1 : 0;
-  return pk;
-}
-
-// Encodes step (*step_base + step_off) into f->enc.  peek: the table sweep of the previous step is still pending.
-static int fit_enqueue_encode(Fit* f, int step_off, bool peek, cudaStream_t st) {
-  const int n = f->bsz;
-  const StepRows sr{f->idx, f->step_base, step_off};
-  const int tb = 256, blocks = (n * f->grid.n_levels + tb - 1) / tb;
-  fit_encode_kernel<<<blocks, tb, 0, st>>>(f->grid, f->tp, f->coords, sr, n, f->enc, f->ld_enc, (size_t)n * f->ld_enc,
-                                           fit_peek_args(f, peek));
+static int fit_launch_sweep(Fit* f, int step_off, bool phase2, cudaStream_t st) {
+  int sg_ = 0, sb_ = 0;
+  fit_sweep_geometry(f, phase2, &sg_, &sb_);
+  fit_adam_table_kernel<<<sg_, sb_, 0, st>>>(f->tb, f->n_table / 4, f->sc_main, f->step_base, step_off, f->wd);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;
 }
 
-// One optimisation step.  Default (f->pipeline == false): encode, GEMM chain, loss, backward, then the dense table sweep,
-// all ordered on the main stream with the independent GEMM chains on side streams.
-// Experimental software-pipelined schedule (f->pipeline == true; exact, parity-tested, but not yet faster because the
-// one-wave sweep leaves no SM slots for the 216 KB GEMM CTAs -- see DESIGN.md):
-//   main stream : GEMM h1, GEMM F, [join residual fwd], loss, dgrad, dgrad, grid backward, [join side chains],
-//                 join sweep(t-1), encode(t+1) with Adam(t) applied on the fly, fork sweep(t)
+// Encodes step (*step_base + step_off) into f->enc from state S_{step - npeek}, applying the npeek pending Adam steps
+// on the fly.
+static int fit_enqueue_encode(Fit* f, int step_off, int npeek, cudaStream_t st) {
+  const int n = f->bsz;
+  const StepRows sr{f->idx, f->step_base, step_off, f->inputs_dev};
+  const int tb = 256, blocks = (n * f->grid.n_levels * 4 + tb - 1) / tb;
+  fit_encode_kernel<<<blocks, tb, 0, st>>>(f->grid, f->tb, nullptr, f->coords, sr, n, f->enc, f->ld_enc,
+                                           (size_t)n * f->ld_enc, f->sc_main, f->wd, npeek);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DVT_OK;
+}
+
+// One optimisation step.
+// Pipelined schedule (f->pipe[phase]): the dense table sweep -- half of a step's time when run in line -- is taken off the
+// critical path entirely.  Sweep(t) runs on stream sD, on its own SMs, beside the chains of steps t+1 and t+2:
+//   main stream : GEMM h1, GEMM F, [join residual fwd], loss, dgrad, dgrad, wait sweep(t-2), grid backward,
+//                 [join side chains], encode(t+1) from S_{t-1} with Adam steps t-1 and t applied on the fly, fork sweep(t)
 //   side B / C  : weight-gradient GEMMs, residual MLP forward / backward, Adam(small params)
-//   side D      : dense table sweep of step t, running beside the whole main chain of step t+1
-// Precondition: f->enc holds the encoding of step t.  Postcondition: f->enc holds the encoding of step t+1 and
-// sweep(t) is pending on sD.
+//   side D      : sweep(t): S_t (buffer t & 1) + g_t -> S_{t+1} (other buffer); re-zeroes the gradient slot of step t-1
+// The on-the-fly updates use the same adam1() arithmetic on the same inputs as the sweep, so the encoded values are
+// bit-identical to a sequential schedule.  Hazards: encode(t+1) reads S_{t-1}, complete since sweep(t-2) was waited for;
+// sweep(t) overwrites the buffer of S_{t-1} and is forked after encode(t+1); the backward of step t writes the ring slot
+// that sweep(t-2) re-zeroed.  Precondition: f->enc holds the encoding of step t.
+// Sequential schedule (f->pipe[phase] == false): encode(t) at the head of the step, sweep(t) on the main stream at its tail.
 static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, int impl) {
   const int n = f->bsz, C = f->C, H1 = C / 2, Hr = C / 4, Lf = f->Lf;
-  const StepRows sr{f->idx, f->step_base, step_off};
+  const StepRows sr{f->idx, f->step_base, step_off, f->inputs_dev};
   const int tb = 256;
   const int enc_blocks = (n * f->grid.n_levels + tb - 1) / tb;
   float* sp = f->sp; float* sg = f->sg;
@@ -982,7 +1038,8 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   fit_gather_rows_kernel<<<n, 192, 0, sB>>>(f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  if (!f->pipeline) FIT_RC(fit_enqueue_encode(f, step_off, /*peek=*/false, st));  // else f->enc is already this step's
+  const bool pipe = f->pipe[phase2 ? 1 : 0];
+  if (!pipe) FIT_RC(fit_enqueue_encode(f, step_off, 0, st));  // else f->enc is already this step's (fit_run)
   if (phase2) {
     FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl));
     FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl));
@@ -1005,8 +1062,11 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   FIT_RC(fork(sB, f->ev[4]));  // dh1 ready
   FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl));           // side B (reads enc)
   FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl));
-  fit_grid_bwd_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->coords, sr, n, f->denc, Lf, f->tg[0], f->tg[1],
-                                                 f->tstamp[0], f->tstamp[1]);
+  // the gradient ring slot of this step was re-zeroed by the sweep of step t-2, which also produced the state the
+  // next encode reads
+  if (pipe && f->epoch_steps >= 2)
+    DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev_sweep[(f->epoch_steps - 2) % 3], 0));
+  fit_grid_bwd_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->coords, sr, n, f->denc, Lf, f->tb);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   if (phase2) {                                                                              // side C
@@ -1018,30 +1078,7 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
     FIT_RC(join(sC, f->ev[5]));
   }
   FIT_RC(join(sB, f->ev[6]));  // all small-parameter gradients complete; enc no longer read by a wgrad
-  if (!f->pipeline) {
-    // ---- sequential schedule: dense table sweep on the main stream, Adam(small) beside it ----
-    FIT_RC(fork(sB, f->ev[7]));
-    const int nv0 = f->n_small / 4;
-    fit_adam_small_kernel<<<(nv0 + 255) / 256, 256, 0, sB>>>(
-        (float4*)f->sp, (float4*)f->sm, (float4*)f->sv, (float4*)f->sg, f->wsplit, nv0, f->G.off / 4,
-        (f->G.off + r8(f->G.rows * f->G.cols)) / 4, f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res, f->step_base,
-        step_off, f->freeze_step, f->wd);
-    DVT_CUDA_OK(cudaGetLastError());
-    count_launch();
-    int sg_ = 0, sb_ = 0;
-    fit_sweep_geometry(&sg_, &sb_);
-    fit_adam_table_kernel<<<sg_, sb_, 0, st>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
-                                                          (float4*)f->tg[0], (float4*)f->tg[1], f->tstamp[0],
-                                                          f->tstamp[1], f->n_table / 4, f->sc_main, f->step_base, step_off,
-                                                          f->wd);
-    DVT_CUDA_OK(cudaGetLastError());
-    count_launch();
-    FIT_RC(join(sB, f->ev[8]));
-    return DVT_OK;
-  }
-  // ---- the previous step's table sweep must be complete before its state is read / the next sweep starts ----
-  if (f->sweep_pending) FIT_RC(join(sD, f->ev[9]));
-  // ---- Adam(small) beside the encode of the NEXT step (Adam step t of the table applied on the fly) ----
+  // ---- Adam(small) on side B, beside the table work ----
   FIT_RC(fork(sB, f->ev[7]));
   const int nv = f->n_small / 4;
   fit_adam_small_kernel<<<(nv + 255) / 256, 256, 0, sB>>>(
@@ -1050,27 +1087,29 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
       step_off, f->freeze_step, f->wd);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  FIT_RC(fit_enqueue_encode(f, step_off + 1, /*peek=*/true, st));
+  if (!pipe) {
+    FIT_RC(fit_launch_sweep(f, step_off, phase2, st));
+    FIT_RC(join(sB, f->ev[8]));
+    f->enc_ready = false;
+    return DVT_OK;
+  }
+  // ---- encode of the NEXT step: one pending Adam step right after a join of the sweeps, two in steady state ----
+  FIT_RC(fit_enqueue_encode(f, step_off + 1, f->epoch_steps == 0 ? 1 : 2, st));
   FIT_RC(join(sB, f->ev[8]));
-  // ---- dense table sweep of this step: forked, joined by the next step (or by fit_sync_sweep) ----
+  // ---- dense table sweep of this step ----
   FIT_RC(fork(sD, f->ev[10]));
-  int sg_ = 0, sb_ = 0;
-  fit_sweep_geometry(&sg_, &sb_);
-  fit_adam_table_kernel<<<sg_, sb_, 0, sD>>>((float4*)f->tp, (float4*)f->tm, (float4*)f->tv,
-                                                        (float4*)f->tg[0], (float4*)f->tg[1], f->tstamp[0], f->tstamp[1],
-                                                        f->n_table / 4, f->sc_main, f->step_base, step_off, f->wd);
-  DVT_CUDA_OK(cudaGetLastError());
-  count_launch();
-  f->sweep_pending = true;
+  FIT_RC(fit_launch_sweep(f, step_off, phase2, sD));
+  DVT_CUDA_OK(cudaEventRecord(f->ev_sweep[f->epoch_steps % 3], sD));
+  f->epoch_steps += 1;
+  f->enc_ready = true;
   return DVT_OK;
 }
 
-// Waits (on `st`) for the pending table sweep.
+// Waits (on `st`) for all pending table sweeps (sD executes them in order: the last event covers the others).
 static int fit_sync_sweep(Fit* f, cudaStream_t st) {
-  if (!f->sweep_pending) return DVT_OK;
-  DVT_CUDA_OK(cudaEventRecord(f->ev[9], f->sD));
-  DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev[9], 0));
-  f->sweep_pending = false;
+  if (f->epoch_steps == 0) return DVT_OK;
+  DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev_sweep[(f->epoch_steps - 1) % 3], 0));
+  f->epoch_steps = 0;
   return DVT_OK;
 }
 
@@ -1079,7 +1118,7 @@ static int fit_capture(Fit* f, bool phase2, int steps, cudaStream_t st, int impl
   const long long before = launch_count();
   DVT_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   int rc = DVT_OK;
-  f->sweep_pending = false;  // graphs start and end with the table up to date
+  f->epoch_steps = 0;  // graphs start and end with the sweeps joined
   for (int i = 0; i < steps && rc == DVT_OK; ++i) rc = fit_enqueue_step(f, i, phase2, st, impl);
   if (rc == DVT_OK) rc = fit_sync_sweep(f, st);  // a capture must join every forked stream
   if (rc == DVT_OK) {
@@ -1115,10 +1154,6 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
   DVT_REQUIRE(count >= 0 && cur + count <= f->num_iters, "fit_run: %d steps from %d exceed the schedule of %d", count, cur,
               f->num_iters);
   const int end = cur + count;
-  if (f->pipeline && count > 0 && !f->enc_ready) {  // first step of a fit: plain encode, no Adam step pending
-    FIT_RC(fit_enqueue_encode(f, 0, /*peek=*/false, st));
-    f->enc_ready = true;
-  }
   if (use_graphs > 0 && use_graphs != f->graph_steps) {
     fit_drop_graphs(f);
     f->graph_steps = use_graphs;
@@ -1127,12 +1162,19 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
     const bool phase2 = cur > f->freeze_step;
     // last step (exclusive) of the current phase within [cur, end)
     const int phase_end = phase2 ? end : std::min(end, f->freeze_step + 1);
+    if (f->pipe[phase2 ? 1 : 0] && !f->enc_ready) {
+      // a pipelined step expects its encoding in f->enc (first step of a fit / after a sequential step): plain encode,
+      // all sweeps are joined here
+      FIT_RC(fit_enqueue_encode(f, 0, 0, st));
+      f->enc_ready = true;
+    }
     if (use_graphs > 0 && cur + use_graphs <= phase_end) {
       cudaGraphExec_t* g = phase2 ? &f->graph2 : &f->graph1;
       long long* nodes = phase2 ? &f->graph2_nodes : &f->graph1_nodes;
       if (!*g) FIT_RC(fit_capture(f, phase2, use_graphs, st, impl, g, nodes));
       DVT_CUDA_OK(cudaGraphLaunch(*g, st));
       count_launch(*nodes);
+      f->enc_ready = f->pipe[phase2 ? 1 : 0];  // what the captured steps leave behind
       cur += use_graphs;
     } else {
       FIT_RC(fit_enqueue_step(f, 0, phase2, st, impl));
@@ -1140,14 +1182,29 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
       FIT_RC(fit_sync_sweep(f, st));
       fit_advance_kernel<<<1, 1, 0, st>>>(f->step_base, 1);
       DVT_CUDA_OK(cudaGetLastError());
-    count_launch();
-  count_launch();
+      count_launch();
       cur += 1;
     }
   }
   FIT_RC(fit_sync_sweep(f, st));
+  f->cur_host = end;
   DVT_CUDA_OK(cudaEventRecord(f->ev_out, st));
   DVT_CUDA_OK(cudaStreamWaitEvent(caller, f->ev_out, 0));
+  return DVT_OK;
+}
+
+// One dense table sweep (the Adam step of the CURRENT device step counter, state buffer ping-pong not advanced) on `st`:
+// the hook bench.py / ncu use to time the dominant HBM-bound kernel alone.  ctas: > 0 persistent 1024-thread CTAs, 0 the
+// many-small-CTA geometry.  The optimiser state is modified: call it after the fit results have been read.
+int fit_sweep_once(Fit* f, int ctas, cudaStream_t st) {
+  DVT_REQUIRE(f->sc_main && f->num_iters > 0, "fit_sweep_once: call fit_begin first");
+  int cur = 0;
+  DVT_CUDA_OK(cudaMemcpy(&cur, f->step_base, 4, cudaMemcpyDeviceToHost));
+  DVT_REQUIRE(cur <= f->num_iters, "fit_sweep_once: step counter %d beyond the schedule", cur);  // sc_main has num_iters + 1 rows
+  const int grid = ctas > 0 ? std::min(ctas, num_sms()) : num_sms() * 8, block = ctas > 0 ? 1024 : 256;
+  fit_adam_table_kernel<<<grid, block, 0, st>>>(f->tb, f->n_table / 4, f->sc_main, f->step_base, 0, f->wd);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
   return DVT_OK;
 }
 
@@ -1178,8 +1235,8 @@ int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, i
   const int C = f->C, H1 = C / 2;
   const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};
-  fit_encode_kernel<<<(n * f->grid.n_levels + 255) / 256, 256, 0, st>>>(f->grid, f->tp, coords, sr, n, f->q_enc, f->ld_enc,
-                                                                       cap * f->ld_enc, fit_peek_args(f, false));
+  fit_encode_kernel<<<(n * f->grid.n_levels * 4 + 255) / 256, 256, 0, st>>>(
+      f->grid, f->tb, f->tb.p[f->cur_host & 1], coords, sr, n, f->q_enc, f->ld_enc, cap * f->ld_enc, nullptr, 0.f, 0);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   FIT_RC(fit_linear(Op{f->q_enc, f->ld_enc, cap * f->ld_enc}, n, f->Lf, Op{f->wsplit + f->W1.off, f->Lf, wp}, H1,
@@ -1243,8 +1300,9 @@ int hashgrid_bwd(int n_levels, const float* scale, const uint32_t* res, const ui
   GridLevels g;
   FIT_RC(levels_from_arrays(&g, n_levels, scale, res, size, offset, hashed));
   const StepRows sr{nullptr, nullptr, 0};
-  fit_grid_bwd_kernel<<<(n * n_levels + 255) / 256, 256, 0, st>>>(g, coords, sr, n, dout, n_levels * FIT_F, gtable, gtable,
-                                                                  nullptr, nullptr);
+  TableBufs tb = {};
+  tb.g[0] = gtable;  // no stamps: plain accumulation
+  fit_grid_bwd_kernel<<<(n * n_levels + 255) / 256, 256, 0, st>>>(g, coords, sr, n, dout, n_levels * FIT_F, tb);
   DVT_CUDA_OK(cudaGetLastError());
   return DVT_OK;
 }

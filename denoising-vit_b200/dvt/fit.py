@@ -104,10 +104,13 @@ class FitEngine:
               "dvt_fit_losses")
         return out
 
-    def query(self, coords: torch.Tensor) -> torch.Tensor:
-        """neural_field(coords): coords [..., 2] in [0,1] -> [..., C] (the `denoised_feats` of the reference)."""
+    def query(self, coords: torch.Tensor, assume_valid: bool = False) -> torch.Tensor:
+        """neural_field(coords): coords [..., 2] in [0,1] -> [..., C] (the `denoised_feats` of the reference).
+        assume_valid: the caller has already range-checked `coords` (the check reads the tensor back, which blocks the
+        host until everything queued before it -- e.g. a whole fit -- has finished)."""
         c = coords.reshape(-1, 2).to(device="cuda", dtype=torch.float32).contiguous()
-        assert c.min() >= 0 and c.max() <= 1, "coordinates should be in [0, 1]"
+        if not assume_valid:
+            assert c.min() >= 0 and c.max() <= 1, "coordinates should be in [0, 1]"
         out = torch.empty((c.shape[0], self.C), device="cuda", dtype=torch.float32)
         check(lib().dvt_fit_query(self._h, ptr(c), c.shape[0], ptr(out), cur_stream()), "dvt_fit_query")
         return out.reshape(*coords.shape[:-1], self.C)
@@ -117,6 +120,10 @@ class FitEngine:
         out = torch.empty_like(r)
         check(lib().dvt_fit_residual(self._h, ptr(r), r.shape[0], ptr(out), cur_stream()), "dvt_fit_residual")
         return out.reshape(raw.shape)
+
+    def sweep_once(self, ctas: int = 0):
+        """Measurement hook (bench.py, ncu): one dense Adam sweep of the table on the current stream."""
+        check(lib().dvt_fit_sweep_once(self._h, ctas, cur_stream()), "dvt_fit_sweep_once")
 
     def fit(self, denoiser, neural_field, bank_feats, bank_coords, idx_stream, *, graph_steps: int = 10, **hyper):
         """Whole per-image fit; returns the per-step loss table [num_iters, 5]."""

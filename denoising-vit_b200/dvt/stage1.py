@@ -43,17 +43,23 @@ class Stage1Pipeline:
         self.field = DVT.NeuralFeatureField(feat_dim=self.C, n_levels=cfg.n_levels).cuda()
         self.engine = FitEngine(self.C, self.h, self.w, cfg.pixel_bsz, self.field.meta)
         self._gen = torch.Generator(device="cuda")
-        self._bank: Optional[torch.Tensor] = None
+        # coordinates of the final query (main_img_denoising.py:121-130), uploaded once: a pageable host-to-device copy
+        # after the fit would block the host until the fit has finished and serialise run_images
+        self._full_coords = make_patch_coordinates(self.h, self.w, 0, 1).to("cuda")
+        assert self._full_coords.min() >= 0 and self._full_coords.max() <= 1
+        self._banks = [None, None]              # double-buffered feature banks (run_images overlaps two images)
         self._stage: Optional[torch.Tensor] = None
+        self._extract_stream: Optional[torch.cuda.Stream] = None
 
     # ---- HP-1 ----------------------------------------------------------------------------------------------
-    def extract_bank(self, views: torch.Tensor) -> torch.Tensor:
-        """views [V, 3, H, W] (cuda, or pinned host memory) -> bank [V, h, w, C] fp32 (cuda).
-        Host views are copied batch by batch on a side stream into two staging buffers, so the copy of batch k+1
-        overlaps the forward of batch k."""
+    def extract_bank(self, views: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """views [V, 3, H, W] (cuda, or pinned host memory) -> bank [V, h, w, C] fp32 (cuda), written into bank buffer
+        `slot` (0 / 1).  Host views are copied batch by batch on a side stream into two staging buffers, so the copy of
+        batch k+1 overlaps the forward of batch k."""
         V = views.shape[0]
-        if self._bank is None or self._bank.shape[0] != V:
-            self._bank = torch.empty((V, self.h, self.w, self.C), device="cuda", dtype=torch.float32)
+        if self._banks[slot] is None or self._banks[slot].shape[0] != V:
+            self._banks[slot] = torch.empty((V, self.h, self.w, self.C), device="cuda", dtype=torch.float32)
+        bank = self._banks[slot]
         bsz = self.cfg.extract_bsz
         starts = list(range(0, V, bsz))
         on_host = not views.is_cuda
@@ -85,10 +91,10 @@ class Stage1Pipeline:
                 x = self._stage[k % 2][:n]
             else:
                 x = views[s0:s0 + n]
-            self.vit.extract_into(x, self.layer_index, self._bank[s0:s0 + n])  # NHWC, no NCHW round trip
+            self.vit.extract_into(x, self.layer_index, bank[s0:s0 + n])  # NHWC, no NCHW round trip
             if on_host:
                 self._consumed[k % 2].record(main)
-        return self._bank
+        return bank
 
     # ---- HP-2 ----------------------------------------------------------------------------------------------
     def denoise(self, bank: torch.Tensor, coords: torch.Tensor, idx_stream: np.ndarray,
@@ -117,6 +123,62 @@ class Stage1Pipeline:
                           freeze_after=cfg.freeze_shared_artifacts_after, weight_decay=cfg.weight_decay,
                           loss_scale=cfg.loss_scale)
         self.engine.run(graph_steps=cfg.graph_steps)
-        full = make_patch_coordinates(self.h, self.w, 0, 1).to("cuda")
-        denoised = self.engine.query(full).reshape(1, self.h, self.w, self.C)
+        denoised = self.engine.query(self._full_coords, assume_valid=True).reshape(1, self.h, self.w, self.C)
         return {"denoised_feats": denoised, "raw": bank[-1], "denoiser": den}
+
+    # ---- both paths, software-pipelined over images -----------------------------------------------------------
+    def run_images(self, n_images: int, views_fn, coords_fn, idx_fn, finalize, events: Optional[list] = None,
+                   overlap: bool = True):
+        """Processes images 0 .. n_images-1.  The bank extraction of image i+1 (HP-1: tensor-core bound, on a low-priority
+        stream) runs beside the fit of image i (HP-2: latency / HBM bound, on the engine's high-priority streams); the fit
+        of an image needs its complete bank, so this is the only overlap the data dependencies allow.
+          views_fn(i)  -> [V, 3, H, W] cuda or pinned-host views       coords_fn(i) -> [V, h, w, 2] global coordinates
+          idx_fn(i)    -> int [num_iters, pixel_bsz] sampled bank rows  finalize(i, out) -> result (may block, e.g. D2H)
+        events: optional list receiving ("hp1" | "hp2", start_event, end_event) per image (timing events recorded on the
+        stream that runs the path).  overlap=False: strictly one image after the other (for A/B measurements)."""
+        if self._extract_stream is None:
+            self._extract_stream = torch.cuda.Stream(priority=0)   # lowest priority: the fit's short kernels go first
+            self._ext_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._fit_done = [torch.cuda.Event(), torch.cuda.Event()]
+        main = torch.cuda.current_stream()
+        sx = self._extract_stream if overlap else main
+        tev = (lambda: torch.cuda.Event(enable_timing=True)) if events is not None else None
+
+        def enqueue_extract(i):
+            slot = i % 2
+            sx.wait_event(self._fit_done[slot])    # the fit that read this bank buffer two images ago
+            with torch.cuda.stream(sx):
+                if tev:
+                    a = tev()
+                    a.record(sx)
+                bank = self.extract_bank(views_fn(i), slot=slot)
+                if tev:
+                    b = tev()
+                    b.record(sx)
+                    events.append(("hp1", a, b))
+                self._ext_done[slot].record(sx)
+            return bank
+
+        for e in self._fit_done:
+            e.record(main)
+        sx.wait_stream(main)                       # inputs produced on the caller's stream
+        results = []
+        bank = enqueue_extract(0)
+        idx = idx_fn(0)
+        for i in range(n_images):
+            main.wait_event(self._ext_done[i % 2])
+            if tev:
+                a = tev()
+                a.record(main)
+            out = self.denoise(bank, coords_fn(i), idx)
+            if tev:
+                b = tev()
+                b.record(main)
+                events.append(("hp2", a, b))
+            self._fit_done[i % 2].record(main)
+            if i + 1 < n_images:                   # enqueued while the GPU runs the fit of image i
+                bank = enqueue_extract(i + 1)
+                idx = idx_fn(i + 1)
+            results.append(finalize(i, out))
+        main.wait_stream(sx)
+        return results

@@ -176,10 +176,15 @@ def _min_cos(a, b):
     return F.cosine_similarity(a.float().reshape(-1, a.shape[-1]), b.float().reshape(-1, b.shape[-1]), dim=-1).min().item()
 
 
-@pytest.mark.parametrize("impl,graph_steps", [(1, 0), (0, 0), (0, 7)], ids=["simt", "tcgen05", "tcgen05-graphs"])
+@pytest.mark.parametrize("impl,graph_steps,pipeline", [(1, 0, 1), (0, 0, 1), (0, 7, 1), (0, 7, 0), (0, 0, 0)],
+                         ids=["simt", "tcgen05", "tcgen05-graphs", "tcgen05-graphs-sequential", "tcgen05-sequential"])
 @pytest.mark.parametrize("name", ["small_L6", "small_L6_ls1", "hashed_L16"])
-def test_fit_matches_reference_golden(name, impl, graph_steps):
+def test_fit_matches_reference_golden(name, impl, graph_steps, pipeline, monkeypatch):
+    """pipeline=1: default schedule (table sweeps run two steps behind the chain, Adam applied on the fly by the
+    encode); pipeline=0: sequential schedule.  Both must reproduce the reference run."""
     from dvt.fit import FitEngine
+    monkeypatch.setenv("DVT_FIT_PIPELINE", str(pipeline))   # read by dvt_fit_create
+    monkeypatch.setenv("DVT_FIT_SWEEP_CTAS", "6,3")         # pipelined in both phases (the default is phase 1 only)
     cfg, z = _golden(name)
     feats, coords, init, idx, den, field, _ = _setup(cfg)
     assert int(idx.sum()) == int(z["idx_checksum"][0])  # same sampling stream as the reference run
@@ -247,3 +252,53 @@ def test_fit_first_steps_update_direction(impl):
         assert cos > 0.9, f"{k}: update direction cosine {cos}"
         assert abs(got.abs().max().item() - ref.abs().max().item()) < 0.2 * ref.abs().max().item() + 1e-6, k
     assert _L().device_error() == 0
+
+
+@pytest.mark.parametrize("sweep_ctas", ["0", "8,4", "4,-1", "-1,0"])
+def test_fit_schedules_agree(sweep_ctas, monkeypatch):
+    """The software-pipelined schedule is an exact re-ordering: after the same steps its table must equal the sequential
+    schedule's up to the run-to-run noise of the floating-point atomics."""
+    from dvt.fit import FitEngine
+    cfg, z = _golden("hashed_L16")
+    outs = []
+    for pipeline in ("0", "1"):
+        monkeypatch.setenv("DVT_FIT_PIPELINE", pipeline)
+        monkeypatch.setenv("DVT_FIT_SWEEP_CTAS", sweep_ctas)
+        feats, coords, init, idx, den, field, _ = _setup(cfg)
+        eng = FitEngine(cfg["C"], cfg["h"], cfg["w"], cfg["bsz"], field.meta)
+        eng.fit(den, field, feats.reshape(-1, cfg["C"]).cuda().contiguous(), coords.reshape(-1, 2).cuda().contiguous(), idx,
+                graph_steps=5, lr=cfg["lr"], min_lr=cfg["min_lr"], warmup_iters=cfg["warmup_iters"],
+                freeze_after=cfg["freeze_after"], weight_decay=cfg["weight_decay"], loss_scale=cfg["loss_scale"])
+        torch.cuda.synchronize()
+        outs.append((eng.get_param("table", init["table"]).cpu() - init["table"], eng.losses().copy()))
+        assert _L().device_error() == 0
+    (ta, la), (tb, lb) = outs
+    cos = F.cosine_similarity(ta.flatten().double(), tb.flatten().double(), dim=0).item()
+    assert cos > 0.9999, f"table update cosine between schedules {cos}"
+    assert np.allclose(la, lb, rtol=1e-3, atol=1e-5)
+
+
+def test_fit_engine_reuse_with_another_bank():
+    """A second fit on the same engine with the bank in ANOTHER buffer (the stage-1 pipeline alternates two) must replay
+    its captured CUDA graphs against the new bank: same result as a fresh engine."""
+    from dvt.fit import FitEngine
+    cfg, z = _golden("small_L6")
+    feats, coords, init, idx, den, field, _ = _setup(cfg)
+    hyper = dict(graph_steps=7, lr=cfg["lr"], min_lr=cfg["min_lr"], warmup_iters=cfg["warmup_iters"],
+                 freeze_after=cfg["freeze_after"], weight_decay=cfg["weight_decay"], loss_scale=cfg["loss_scale"])
+    bank_a = (feats.reshape(-1, cfg["C"]) * -0.5 + 0.3).cuda().contiguous()     # some other image
+    bank_b = feats.reshape(-1, cfg["C"]).cuda().contiguous()
+    coords_a = coords.reshape(-1, 2).flip(0).cuda().contiguous()
+    coords_b = coords.reshape(-1, 2).cuda().contiguous()
+    assert bank_a.data_ptr() != bank_b.data_ptr() and coords_a.data_ptr() != coords_b.data_ptr()
+    used = FitEngine(cfg["C"], cfg["h"], cfg["w"], cfg["bsz"], field.meta)
+    used.fit(den, field, bank_a, coords_a, idx, **hyper)
+    used.fit(den, field, bank_b, coords_b, idx, **hyper)       # graphs captured by the first fit are replayed here
+    fresh = FitEngine(cfg["C"], cfg["h"], cfg["w"], cfg["bsz"], field.meta)
+    fresh.fit(den, field, bank_b, coords_b, idx, **hyper)
+    torch.cuda.synchronize()
+    assert _L().device_error() == 0
+    qa, qb = used.query(coords[-1:].cuda()), fresh.query(coords[-1:].cuda())
+    assert _min_cos(qa.cpu(), qb.cpu()) > 0.9999
+    assert _min_cos(qa.cpu(), torch.from_numpy(z["denoised_feats"])) > 0.999
+    assert np.allclose(used.losses(), fresh.losses(), rtol=1e-3, atol=1e-5)

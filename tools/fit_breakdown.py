@@ -20,18 +20,35 @@ def main():
     ap.add_argument("--iters", type=int, default=400)
     ap.add_argument("--graph-steps", type=int, default=10)
     ap.add_argument("--views", type=int, default=769)
+    ap.add_argument("--configs", default="",
+                    help="';'-separated engine configurations 'pipeline:sweep_ctas[:graph_steps]', e.g. '1:48,32;0:0:20'")
+    ap.add_argument("--graphs-only", action="store_true")
     a = ap.parse_args()
     C, h, w, V, bsz = 768, 37, 37, a.views, 2048
     field = DVT.NeuralFeatureField(feat_dim=C, n_levels=16)
     den = DVT.SingleImageDenoiser(h, w, C)
-    eng = FitEngine(C, h, w, bsz, field.meta)
     g = torch.Generator(device="cuda").manual_seed(0)
     bank = torch.randn(V * h * w, C, device="cuda", generator=g)
     coords = torch.rand(V * h * w, 2, device="cuda", generator=g)
     idx = np.random.RandomState(0).randint(0, V * h * w, (a.iters, bsz))
-    eng.load_modules(den, field)
+    for cfg in (a.configs.split(";") if a.configs else [""]):
+        gsteps = a.graph_steps
+        if cfg:
+            parts = cfg.split(":")
+            os.environ["DVT_FIT_PIPELINE"] = parts[0]
+            os.environ["DVT_FIT_SWEEP_CTAS"] = parts[1]
+            if len(parts) > 2:
+                gsteps = int(parts[2])
+            print(f"== pipeline={parts[0]} sweep_ctas={parts[1]} graph_steps={gsteps}", flush=True)
+        eng = FitEngine(C, h, w, bsz, field.meta)
+        eng.load_modules(den, field)
+        time_engine(eng, a, bank, coords, idx, (gsteps,) if a.graphs_only else (gsteps, 0))
+        del eng
+
+
+def time_engine(eng, a, bank, coords, idx, graph_modes):
     hyper = dict(lr=0.01, min_lr=0.001, warmup_iters=a.iters // 10, freeze_after=0.5, weight_decay=1e-5, loss_scale=1024.0)
-    for gs in (a.graph_steps, 0):
+    for gs in graph_modes:
         eng.begin(bank, coords, idx, **hyper)   # warm-up pass: graph capture / instantiation, first-touch, clocks
         eng.run(a.iters, graph_steps=gs)
         torch.cuda.synchronize()
