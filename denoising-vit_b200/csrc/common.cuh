@@ -118,6 +118,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
 }
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with launch_k(pdl = true, ...) may start -- block scheduling,
+// barrier / TMEM set-up -- while the previous kernel of its stream is still running; pdl_wait() blocks until that kernel
+// has completed and its writes are visible, pdl_trigger() lets the NEXT kernel of the stream start its own prologue.
+// Both are no-ops in a kernel that was launched without the attribute.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // proxy fences
 // ------------------------------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (TMA store / tcgen05.mma operand reads)

@@ -12,12 +12,13 @@
 //   GEMM  dh1 = (dpred W2) * relu'        GEMM  dW2|db2 += dpred^T [h1|1]   GEMM dW1|db1 += dh1^T [enc|1]
 //   GEMM  denc = dh1 W1                   grid backward (vector atomics into the dense table gradient)
 //   [+ residual MLP backward, 5 GEMMs]    Adam(table) dense sweep           Adam(small params) + bf16 mirrors
-// All GEMMs run on tcgen05 (gemm.cu) as 3xTF32 products of fp32 hi/lo planes (fp32-accurate: bf16 operands cannot
-// hold the cosine >= 0.999 parity bar); weight-gradient GEMMs read the activations as MN-major
+// All GEMMs run on tcgen05 (gemm.cu) as 3xTF32 products (fp32-accurate: bf16 operands cannot hold the cosine >= 0.999
+// parity bar; the kernel splits the fp32 operand tiles into TF32 hi / lo parts in shared memory, so
+// activations and weights exist once, as plain fp32); weight-gradient GEMMs read the activations as MN-major
 // operands, so no transposed copies exist; bias gradients come from a ones column appended to the activation buffers.
 //
 // HBM layout: table p/m/v/g as four fp32 arrays of n_entries*8; "small" params (field MLP, G as [h*w, C],
-// residual MLP) in one flat fp32 buffer with identically laid out m / v / grad buffers and TF32 hi/lo operand planes.
+// residual MLP) in one flat fp32 buffer with identically laid out m / v / grad buffers.
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -146,11 +147,13 @@ __device__ __forceinline__ void adam8(float4& pa, float4& pb, float4& ma, float4
 // the encoded step is s, the state that is read is S_{s - npeek}.  table_fixed != nullptr: read that table (query mode).
 __global__ void __launch_bounds__(256)
 fit_encode_kernel(GridLevels g, TableBufs tb, const float* __restrict__ table_fixed, const float* __restrict__ coords,
-                  StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane,
+                  StepRows sr, int n, float* __restrict__ enc, int ld_enc,
                   const AdamScalars* __restrict__ sc, float wd, int npeek) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int q = t >> 2, k = t & 3;
   if (q >= n * g.n_levels) return;  // n % 8 == 0: warps are either complete or empty
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
   const int i = q % n, l = q / n;
   const int* rows = sr.rows(n);
   const int r = rows ? rows[i] : i;
@@ -197,16 +200,11 @@ fit_encode_kernel(GridLevels g, TableBufs tb, const float* __restrict__ table_fi
     acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 1);
     acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 2);
   }
-  // lane k stores one float4: k = 0/1 the hi plane (features 0-3 / 4-7), k = 2/3 the lo plane
-  float o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float a = (k & 1) ? acc[4 + j] : acc[j];
-    const float hi = tf32_hi(a);
-    o[j] = (k & 2) ? a - hi : hi;
+  // lanes 0 / 1 of the quad store features 0-3 / 4-7
+  if (k < 2) {
+    float* dst = enc + (size_t)i * ld_enc + l * FIT_F + k * 4;
+    *reinterpret_cast<float4*>(dst) = k ? make_float4(acc[4], acc[5], acc[6], acc[7]) : make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
-  float* dst = enc + (size_t)i * ld_enc + l * FIT_F + (k & 1) * 4 + ((k & 2) ? plane : 0);
-  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // fp32 encode (unit-test entry point: bit-level check of indices / weights against the oracle)
@@ -247,6 +245,8 @@ __global__ void fit_grid_bwd_kernel(GridLevels g, const float* __restrict__ coor
                                     const float* __restrict__ denc, int ld_denc, TableBufs tb) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * g.n_levels) return;
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
   const int i = t % n, l = t / n;
   const int* rows = sr.rows(n);
   const int r = rows ? rows[i] : i;
@@ -273,18 +273,16 @@ __global__ void fit_grid_bwd_kernel(GridLevels g, const float* __restrict__ coor
   }
 }
 
-// gather bank rows (fp32) -> hi/lo planes [n, ld] (input of the residual MLP)
+// gather bank rows (fp32) -> [n, ld] (loss target; input of the residual MLP)
 __global__ void fit_gather_rows_kernel(const float* __restrict__ bank, int C, StepRows sr, int n,
-                                       float* __restrict__ out, int ld, size_t plane) {
+                                       float* __restrict__ out, int ld) {
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
   const int i = blockIdx.x;
   const int* rows = sr.rows(n);
   const float4* src = reinterpret_cast<const float4*>(sr.bank(bank) + (size_t)(rows ? rows[i] : i) * C);
   for (int c4 = threadIdx.x; c4 < C / 4; c4 += blockDim.x) {
-    const float4 v = __ldg(src + c4);
-    const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    float* dst = out + (size_t)i * ld + c4 * 4;
-    *reinterpret_cast<float4*>(dst) = hi;
-    *reinterpret_cast<float4*>(dst + plane) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    *reinterpret_cast<float4*>(out + (size_t)i * ld + c4 * 4) = __ldg(src + c4);
   }
 }
 
@@ -293,17 +291,15 @@ __global__ void fit_gather_rows_kernel(const float* __restrict__ bank, int C, St
 // losses[5] (this step's slots) accumulates: total, patch_l2, cosine, residual, residual_sparsity.
 // ----------------------------------------------------------------------------------------------------
 struct LossArgs {
-  const float* raw;         // [2 planes][n, ld_raw] raw ViT features of the sampled rows (hi / lo, gathered on a side stream:
-                            //  random 3 KB rows of a 3 GB bank are TLB misses that must not sit on the critical path)
+  const float* raw;         // [n, ld_raw] raw ViT features of the sampled rows (gathered on a side stream: random 3 KB
+                            //  rows of a 3 GB bank are TLB misses that must not sit on the critical path)
   int ld_raw;
-  size_t raw_plane;
   StepRows sr;              // bank rows of this step
   const float* F;           // [n, C] field output
   const float* G;           // [hw, C] shared artifact map (fp32 master)
   const float* R;           // [n, C] residual prediction or nullptr (phase 1)
-  float* dpred;             // [2 planes][n, C] (hi / lo)
-  float* dR;                // [2 planes][n, C] or nullptr
-  size_t plane;             // n * C
+  float* dpred;             // [n, C]
+  float* dR;                // [n, C] or nullptr
   float* gG;                // [hw, C] gradient accumulator or nullptr (G frozen)
   float* losses;            // [num_iters, 5]; this step's slots are used
   int n, C, hw;
@@ -313,6 +309,8 @@ struct LossArgs {
 // NV = float4 per lane (ceil(C / 128)); all global loads of a row are issued before the first use.
 template <int NV, bool HAS_R>
 __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
   const int row_raw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const bool row_ok = row_raw < a.n;       // (whole warps; the CTA still meets at the __syncthreads below)
@@ -322,14 +320,13 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
   float* losses = a.losses + (size_t)a.sr.step() * 5;
   const int cell = br % a.hw;  // exact (r, c) of the patch inside its view: the "shared artifact coordinate"
   const float4* raw4 = reinterpret_cast<const float4*>(a.raw + (size_t)row * a.ld_raw);
-  const float4* raw4lo = reinterpret_cast<const float4*>(a.raw + a.raw_plane + (size_t)row * a.ld_raw);
   const float4* F4 = reinterpret_cast<const float4*>(a.F + (size_t)row * C);
   const float4* G4 = reinterpret_cast<const float4*>(a.G + (size_t)cell * C);
   const float4* R4 = HAS_R ? reinterpret_cast<const float4*>(a.R + (size_t)row * C) : nullptr;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 pred[NV], raw[NV], rp[HAS_R ? NV : 1];
   {
-    float4 f[NV], gg[NV], rl[NV];
+    float4 f[NV], gg[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {  // loads only
       const int v = lane + 32 * i;
@@ -337,12 +334,10 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       f[i] = ok ? F4[v] : z4;
       gg[i] = ok ? __ldg(G4 + v) : z4;
       raw[i] = ok ? raw4[v] : z4;
-      rl[i] = ok ? raw4lo[v] : z4;
       if (HAS_R) rp[i] = ok ? R4[v] : z4;
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      raw[i] = make_float4(raw[i].x + rl[i].x, raw[i].y + rl[i].y, raw[i].z + rl[i].z, raw[i].w + rl[i].w);  // hi + lo == raw
       pred[i] = make_float4(f[i].x + gg[i].x, f[i].y + gg[i].y, f[i].z + gg[i].z, f[i].w + gg[i].w);
       if (HAS_R) { pred[i].x += rp[i].x; pred[i].y += rp[i].y; pred[i].z += rp[i].z; pred[i].w += rp[i].w; }
     }
@@ -382,12 +377,7 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
     d.y = k_mse * (p.y - r.y) + k_cr * r.y + k_cp * p.y;
     d.z = k_mse * (p.z - r.z) + k_cr * r.z + k_cp * p.z;
     d.w = k_mse * (p.w - r.w) + k_cr * r.w + k_cp * p.w;
-    {
-      const float4 hi = make_float4(tf32_hi(d.x), tf32_hi(d.y), tf32_hi(d.z), tf32_hi(d.w));
-      float* dp = a.dpred + (size_t)row * C + v * 4;
-      *reinterpret_cast<float4*>(dp) = hi;
-      *reinterpret_cast<float4*>(dp + a.plane) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
-    }
+    *reinterpret_cast<float4*>(a.dpred + (size_t)row * C + v * 4) = d;
     if (a.gG) {
       float* dst = a.gG + (size_t)cell * C + v * 4;
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
@@ -403,10 +393,7 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       auto sgn = [](float x) { return (float)((x > 0.f) - (x < 0.f)); };
       const float4 dr = make_float4(k1 * ex + k2 * sgn(q.x), k1 * ey + k2 * sgn(q.y), k1 * ez + k2 * sgn(q.z),
                                     k1 * ew + k2 * sgn(q.w));
-      const float4 hi = make_float4(tf32_hi(dr.x), tf32_hi(dr.y), tf32_hi(dr.z), tf32_hi(dr.w));
-      float* dp = a.dR + (size_t)row * C + v * 4;
-      *reinterpret_cast<float4*>(dp) = hi;
-      *reinterpret_cast<float4*>(dp + a.plane) = make_float4(dr.x - hi.x, dr.y - hi.y, dr.z - hi.z, dr.w - hi.w);
+      *reinterpret_cast<float4*>(a.dR + (size_t)row * C + v * 4) = dr;
     }
   }
   if (HAS_R) {
@@ -438,22 +425,23 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
 }
 
 template <bool HAS_R>
-static int launch_loss_nv(const LossArgs& la, int blocks, int tb, cudaStream_t st) {
+static int launch_loss_nv(const LossArgs& la, int blocks, int tb, cudaStream_t st, bool pdl) {
   const int nv = (la.C / 4 + 31) / 32;
-  if (nv <= 1) fit_loss_kernel<1, HAS_R><<<blocks, tb, 0, st>>>(la);
-  else if (nv <= 2) fit_loss_kernel<2, HAS_R><<<blocks, tb, 0, st>>>(la);
-  else if (nv <= 3) fit_loss_kernel<3, HAS_R><<<blocks, tb, 0, st>>>(la);
-  else if (nv <= 6) fit_loss_kernel<6, HAS_R><<<blocks, tb, 0, st>>>(la);
-  else if (nv <= 8) fit_loss_kernel<8, HAS_R><<<blocks, tb, 0, st>>>(la);
-  else fit_loss_kernel<12, HAS_R><<<blocks, tb, 0, st>>>(la);
+  const dim3 g(blocks), b(tb);
+  if (nv <= 1) DVT_CUDA_OK(launch_k(pdl, fit_loss_kernel<1, HAS_R>, g, b, 0, st, la));
+  else if (nv <= 2) DVT_CUDA_OK(launch_k(pdl, fit_loss_kernel<2, HAS_R>, g, b, 0, st, la));
+  else if (nv <= 3) DVT_CUDA_OK(launch_k(pdl, fit_loss_kernel<3, HAS_R>, g, b, 0, st, la));
+  else if (nv <= 6) DVT_CUDA_OK(launch_k(pdl, fit_loss_kernel<6, HAS_R>, g, b, 0, st, la));
+  else if (nv <= 8) DVT_CUDA_OK(launch_k(pdl, fit_loss_kernel<8, HAS_R>, g, b, 0, st, la));
+  else DVT_CUDA_OK(launch_k(pdl, fit_loss_kernel<12, HAS_R>, g, b, 0, st, la));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;
 }
 
-static int launch_loss(const LossArgs& la, cudaStream_t st) {
+static int launch_loss(const LossArgs& la, cudaStream_t st, bool pdl) {
   const int tb = 256, blocks = (la.n * 32 + tb - 1) / tb;
-  return la.R ? launch_loss_nv<true>(la, blocks, tb, st) : launch_loss_nv<false>(la, blocks, tb, st);
+  return la.R ? launch_loss_nv<true>(la, blocks, tb, st, pdl) : launch_loss_nv<false>(la, blocks, tb, st, pdl);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -475,6 +463,8 @@ constexpr int ADAM_UNROLL = 2;
 __global__ void __launch_bounds__(1024, 1)
 fit_adam_table_kernel(TableBufs tb, size_t nvec, const AdamScalars* __restrict__ sc, const int* __restrict__ step_base,
                       int step_off, float wd) {
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
   const int step = *step_base + step_off;
   const int src = step & 1, slot = mod3(step), slot_prev = mod3(step + 2);
   const float4* __restrict__ p = reinterpret_cast<const float4*>(DVT_SEL2(tb.p, src));
@@ -537,10 +527,12 @@ fit_adam_table_kernel(TableBufs tb, size_t nvec, const AdamScalars* __restrict__
 
 // small params: one flat buffer; [g_lo, g_hi) is G, [r_lo, r_hi) the residual MLP, the rest the field MLP.
 __global__ void fit_adam_small_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
-                                      float4* __restrict__ g, float* __restrict__ wsplit, int nvec, int g_lo,
+                                      float4* __restrict__ g, int nvec, int g_lo,
                                       int g_hi, int r_lo, int r_hi, const AdamScalars* __restrict__ sc_main,
                                       const AdamScalars* __restrict__ sc_res, const int* __restrict__ step_base,
                                       int step_off, int freeze_step, float wd) {
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
   const int step = *step_base + step_off;
   const bool phase2 = step > freeze_step;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
@@ -555,12 +547,6 @@ __global__ void fit_adam_small_kernel(float4* __restrict__ p, float4* __restrict
     adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.inv_bc2_sqrt);
     p[i] = pp; m[i] = mm; v[i] = vv;
     g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!is_g) {  // GEMM operand planes of the weights
-      const float4 hi = make_float4(tf32_hi(pp.x), tf32_hi(pp.y), tf32_hi(pp.z), tf32_hi(pp.w));
-      *reinterpret_cast<float4*>(wsplit + (size_t)i * 4) = hi;
-      *reinterpret_cast<float4*>(wsplit + (size_t)(nvec + i) * 4) =
-          make_float4(pp.x - hi.x, pp.y - hi.y, pp.z - hi.z, pp.w - hi.w);
-    }
   }
 }
 
@@ -580,13 +566,6 @@ __global__ void fit_transpose_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-__global__ void fit_split_kernel(const float* __restrict__ p, float* __restrict__ wsplit, size_t n) {
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-    const float v = p[e], hi = tf32_hi(v);
-    wsplit[e] = hi;
-    wsplit[n + e] = v - hi;
-  }
-}
 
 __global__ void fit_coord_range_kernel(const float* __restrict__ coords, size_t n2, int* __restrict__ bad) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
@@ -617,11 +596,11 @@ struct Fit {
   cudaEvent_t ev_sweep[3] = {};                // completion of the sweep launched at epoch step i (slot i % 3)
   int epoch_steps = 0;                         // pipelined steps enqueued since the sweeps were last joined
   bool enc_ready = false;                      // f->enc already holds the encoding of the next step
+  bool pdl = false;                            // programmatic dependent launch along the kernel chains of a step
   bool pipe[2] = {true, true};                 // software-pipelined table sweep in phase 1 / 2 (see fit_enqueue_step)
   int sweep_ctas[2] = {0, 0};                  // persistent sweep CTAs in phase 1 / 2 (0 = many small CTAs)
   float *sp = nullptr, *sm = nullptr, *sv = nullptr, *sg = nullptr;
-  float* wsplit = nullptr;  // [2][n_small] TF32 hi / lo planes of the small params (x3 GEMM operands)
-  // activations: GEMM operands are stored as two fp32 planes (hi, lo), plane stride = bsz * ld
+  // activations (plain fp32; the x3 GEMMs split them on the fly)
   float *enc = nullptr, *h1 = nullptr, *dpred = nullptr, *dh1 = nullptr;
   float *Fout = nullptr, *denc = nullptr;
   float *rawb = nullptr, *r1 = nullptr, *r2 = nullptr, *dR = nullptr, *dr2 = nullptr, *dr1 = nullptr;
@@ -697,6 +676,9 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
       const int got = sscanf(se, "%d,%d", &a, &b);
       if (got >= 1) { cfg[0] = a; cfg[1] = got >= 2 ? b : a; }
     }
+    //   DVT_FIT_PDL=1               programmatic dependent launch along the kernel chains of a step
+    const char* pd = getenv("DVT_FIT_PDL");
+    f->pdl = pd && pd[0] == '1';  // opt-in until validated on the GPU
     const char* pe = getenv("DVT_FIT_PIPELINE");
     const bool off = pe && pe[0] == '0';
     for (int q = 0; q < 2; ++q) {
@@ -729,12 +711,12 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
     A((void**)&f->tb.g[q], f->n_table * 4); A((void**)&f->tb.stamp[q], f->n_table / FIT_F * 4);
   }
   A((void**)&f->sp, (size_t)off * 4); A((void**)&f->sm, (size_t)off * 4); A((void**)&f->sv, (size_t)off * 4);
-  A((void**)&f->sg, (size_t)off * 4); A((void**)&f->wsplit, (size_t)off * 8);
+  A((void**)&f->sg, (size_t)off * 4);
   const size_t n = bsz;
-  A((void**)&f->enc, n * f->ld_enc * 8); A((void**)&f->h1, n * f->ld_h1 * 8); A((void**)&f->dpred, n * C * 8);
-  A((void**)&f->dh1, n * H1 * 8); A((void**)&f->Fout, n * C * 4); A((void**)&f->denc, n * f->Lf * 4);
-  A((void**)&f->rawb, n * f->ld_raw * 8); A((void**)&f->r1, n * f->ld_r * 8); A((void**)&f->r2, n * f->ld_r * 8);
-  A((void**)&f->dR, n * C * 8); A((void**)&f->dr2, n * Hr * 8); A((void**)&f->dr1, n * Hr * 8);
+  A((void**)&f->enc, n * f->ld_enc * 4); A((void**)&f->h1, n * f->ld_h1 * 4); A((void**)&f->dpred, n * C * 4);
+  A((void**)&f->dh1, n * H1 * 4); A((void**)&f->Fout, n * C * 4); A((void**)&f->denc, n * f->Lf * 4);
+  A((void**)&f->rawb, n * f->ld_raw * 4); A((void**)&f->r1, n * f->ld_r * 4); A((void**)&f->r2, n * f->ld_r * 4);
+  A((void**)&f->dR, n * C * 4); A((void**)&f->dr2, n * Hr * 4); A((void**)&f->dr1, n * Hr * 4);
   A((void**)&f->Rout, n * C * 4); A((void**)&f->step_base, sizeof(int));
   A((void**)&f->inputs_dev, sizeof(FitInputs));
   if (rc) { for (void* p : f->owned) cudaFree(p); delete f; return rc; }
@@ -917,45 +899,43 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   f->epoch_steps = 0;
   DVT_CUDA_OK(cudaMemset(f->sm, 0, (size_t)f->n_small * 4)); DVT_CUDA_OK(cudaMemset(f->sv, 0, (size_t)f->n_small * 4));
   DVT_CUDA_OK(cudaMemset(f->sg, 0, (size_t)f->n_small * 4));
-  fit_split_kernel<<<256, 256>>>(f->sp, f->wsplit, (size_t)f->n_small);
-  DVT_CUDA_OK(cudaGetLastError());
   DVT_CUDA_OK(cudaDeviceSynchronize());
   return DVT_OK;
 }
 
 #define FIT_RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
-// GEMM operands of the fit are fp32 hi/lo plane pairs; all products are 3xTF32 (fp32-accurate, gemm.cu "x3").
+// GEMM operands of the fit are plain fp32 matrices; all products are 3xTF32 (fp32-accurate, gemm.cu "x3").
 struct Op {
   const float* p;
   int ld;
-  size_t plane;
 };
 
-// Y = act(X W^T + b):  X [M, K] planes, W [N, K] planes.  split_out: Y is written as hi/lo planes (feeds a GEMM).
-static int fit_linear(Op X, int M, int K, Op W, int N, const float* bias, int act, float* out, int ldo, size_t out_plane,
-                      bool split_out, cudaStream_t st, int impl) {
+// Y = act(X W^T + b):  X [M, K], W [N, K]
+static int fit_linear(Op X, int M, int K, Op W, int N, const float* bias, int act, float* out, int ldo, cudaStream_t st,
+                      int impl, bool pdl = false) {
   GemmEpi e;
-  e.bias = bias; e.act = act; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
-  e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
+  e.bias = bias; e.act = act; e.out = out; e.ldo = ldo;
+  e.out_mode = OUT_F32;
   GemmShape s{M, N, K, 1};
-  s.x3 = 1; s.plane_a = X.plane; s.plane_b = W.plane;
+  s.x3 = 1; s.pdl = pdl;
   return launch_gemm_tn(X.p, X.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
 // dX = (dY . W) * (H > 0):  dY [M, Nout] K-major A; W stored [Nout, Kin] = MN-major B with N = Kin
 static int fit_dgrad(Op dY, int M, int Nout, Op W, int Kin, const float* Hmask, int ldmask, float* out, int ldo,
-                     size_t out_plane, bool split_out, cudaStream_t st, int impl) {
+                     cudaStream_t st, int impl, bool pdl = false) {
   GemmEpi e;
-  e.mask_f32 = Hmask; e.ldmask = ldmask; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
-  e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
+  e.mask_f32 = Hmask; e.ldmask = ldmask; e.out = out; e.ldo = ldo;
+  e.out_mode = OUT_F32;
   GemmShape s{M, Kin, Nout, 1};
-  s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = W.plane;
+  s.b_mn = 1; s.x3 = 1; s.pdl = pdl;
   return launch_gemm_tn(dY.p, dY.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
 // dW[Nout, Kin] (+ db[Nout]) += dY^T . [X | 1]:  dY stored [n, Nout] (MN-major A), X stored [n, Kin + ones] (MN-major B)
-static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb, cudaStream_t st, int impl) {
+static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb, cudaStream_t st, int impl,
+                     bool pdl = false) {
   GemmEpi e;
   e.out = gW; e.ldo = Kin; e.out_mode = OUT_F32_ATOMIC; e.last_col_out = gb;
   // split-K so that (output tiles x splits) fills the SMs once: tiles are 128 x 64, k-blocks 32 samples
@@ -963,7 +943,7 @@ static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb
   const int tiles = ((Nout + 127) / 128) * ((Kin + 1 + 63) / 64);
   int splits = std::max(1, std::min(num_sms() / std::max(tiles, 1), kb / 4));
   GemmShape s{Nout, Kin + 1, n, splits};
-  s.a_mn = 1; s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = X.plane;
+  s.a_mn = 1; s.b_mn = 1; s.x3 = 1; s.pdl = pdl;
   return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
 }
 
@@ -978,7 +958,8 @@ static void fit_sweep_geometry(const Fit* f, bool phase2, int* grid, int* block)
 static int fit_launch_sweep(Fit* f, int step_off, bool phase2, cudaStream_t st) {
   int sg_ = 0, sb_ = 0;
   fit_sweep_geometry(f, phase2, &sg_, &sb_);
-  fit_adam_table_kernel<<<sg_, sb_, 0, st>>>(f->tb, f->n_table / 4, f->sc_main, f->step_base, step_off, f->wd);
+  DVT_CUDA_OK(launch_k(f->pdl, fit_adam_table_kernel, dim3(sg_), dim3(sb_), 0, st, f->tb, f->n_table / 4, f->sc_main,
+                       f->step_base, step_off, f->wd));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;
@@ -990,8 +971,8 @@ static int fit_enqueue_encode(Fit* f, int step_off, int npeek, cudaStream_t st) 
   const int n = f->bsz;
   const StepRows sr{f->idx, f->step_base, step_off, f->inputs_dev};
   const int tb = 256, blocks = (n * f->grid.n_levels * 4 + tb - 1) / tb;
-  fit_encode_kernel<<<blocks, tb, 0, st>>>(f->grid, f->tb, nullptr, f->coords, sr, n, f->enc, f->ld_enc,
-                                           (size_t)n * f->ld_enc, f->sc_main, f->wd, npeek);
+  DVT_CUDA_OK(launch_k(f->pdl, fit_encode_kernel, dim3(blocks), dim3(tb), 0, st, f->grid, f->tb, nullptr, f->coords, sr, n,
+                       f->enc, f->ld_enc, f->sc_main, f->wd, npeek));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;
@@ -1015,14 +996,12 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   const int tb = 256;
   const int enc_blocks = (n * f->grid.n_levels + tb - 1) / tb;
   float* sp = f->sp; float* sg = f->sg;
-  const size_t wp = (size_t)f->n_small;  // weight plane stride
-  auto W = [&](const Seg& sgm) { return Op{f->wsplit + sgm.off, sgm.cols, wp}; };
-  const size_t p_enc = (size_t)n * f->ld_enc, p_h1 = (size_t)n * f->ld_h1, p_nc = (size_t)n * C, p_nh = (size_t)n * H1;
-  const size_t p_raw = (size_t)n * f->ld_raw, p_r = (size_t)n * f->ld_r, p_nr = (size_t)n * Hr;
-  const Op enc{f->enc, f->ld_enc, p_enc}, h1{f->h1, f->ld_h1, p_h1}, dpred{f->dpred, C, p_nc}, dh1{f->dh1, H1, p_nh};
-  const Op rawb{f->rawb, f->ld_raw, p_raw}, r1{f->r1, f->ld_r, p_r}, r2{f->r2, f->ld_r, p_r};
-  const Op dR{f->dR, C, p_nc}, dr2{f->dr2, Hr, p_nr}, dr1{f->dr1, Hr, p_nr};
+  auto W = [&](const Seg& sgm) { return Op{f->sp + sgm.off, sgm.cols}; };  // weights: the fp32 masters themselves
+  const Op enc{f->enc, f->ld_enc}, h1{f->h1, f->ld_h1}, dpred{f->dpred, C}, dh1{f->dh1, H1};
+  const Op rawb{f->rawb, f->ld_raw}, r1{f->r1, f->ld_r}, r2{f->r2, f->ld_r};
+  const Op dR{f->dR, C}, dr2{f->dr2, Hr}, dr1{f->dr1, Hr};
   cudaStream_t sB = f->sB, sC = f->sC, sD = f->sD;
+  const bool pdl = f->pdl;
   auto fork = [&](cudaStream_t to, cudaEvent_t e) -> int {
     DVT_CUDA_OK(cudaEventRecord(e, st));
     DVT_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
@@ -1035,56 +1014,56 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   };
   // ---- forward ----
   FIT_RC(fork(sB, f->ev[0]));  // side B: gather the sampled bank rows (+ residual MLP forward in phase 2)
-  fit_gather_rows_kernel<<<n, 192, 0, sB>>>(f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw);
+  DVT_CUDA_OK(launch_k(pdl, fit_gather_rows_kernel, dim3(n), dim3(192), 0, sB, f->bank, C, sr, n, f->rawb, f->ld_raw));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   const bool pipe = f->pipe[phase2 ? 1 : 0];
   if (!pipe) FIT_RC(fit_enqueue_encode(f, step_off, 0, st));  // else f->enc is already this step's (fit_run)
   if (phase2) {
-    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl));
-    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl));
-    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl));
+    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, sB, impl, pdl));
+    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, sB, impl, pdl));
+    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, sB, impl, pdl));
   }
-  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl));
-  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl));
+  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, st, impl, pdl));
+  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, st, impl, pdl));
   FIT_RC(join(sB, f->ev[1]));
   // ---- loss + d pred ----
   LossArgs la;
-  la.raw = f->rawb; la.ld_raw = f->ld_raw; la.raw_plane = p_raw; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
-  la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.plane = p_nc; la.gG = phase2 ? nullptr : sg + f->G.off;
+  la.raw = f->rawb; la.ld_raw = f->ld_raw; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
+  la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.gG = phase2 ? nullptr : sg + f->G.off;
   la.losses = f->losses; la.n = n; la.C = C; la.hw = f->hw; la.loss_scale = f->loss_scale;
-  FIT_RC(launch_loss(la, st));
+  FIT_RC(launch_loss(la, st, pdl));
   // ---- backward ----
   FIT_RC(fork(sB, f->ev[2]));
   if (phase2) FIT_RC(fork(sC, f->ev[3]));
-  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl));          // side B
-  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl));  // main
+  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl, pdl));          // side B
+  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, st, impl, pdl));  // main
   FIT_RC(fork(sB, f->ev[4]));  // dh1 ready
-  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl));           // side B (reads enc)
-  FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl));
+  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl, pdl));           // side B (reads enc)
+  FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, st, impl, pdl));
   // the gradient ring slot of this step was re-zeroed by the sweep of step t-2, which also produced the state the
   // next encode reads
   if (pipe && f->epoch_steps >= 2)
     DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev_sweep[(f->epoch_steps - 2) % 3], 0));
-  fit_grid_bwd_kernel<<<enc_blocks, tb, 0, st>>>(f->grid, f->coords, sr, n, f->denc, Lf, f->tb);
+  DVT_CUDA_OK(launch_k(pdl, fit_grid_bwd_kernel, dim3(enc_blocks), dim3(tb), 0, st, f->grid, f->coords, sr, n, f->denc, Lf,
+                       f->tb));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   if (phase2) {                                                                              // side C
-    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, sC, impl));
-    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sC, impl));
-    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, sC, impl));
-    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sC, impl));
-    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl));
+    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, sC, impl, pdl));
+    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sC, impl, pdl));
+    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, sC, impl, pdl));
+    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sC, impl, pdl));
+    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl, pdl));
     FIT_RC(join(sC, f->ev[5]));
   }
   FIT_RC(join(sB, f->ev[6]));  // all small-parameter gradients complete; enc no longer read by a wgrad
   // ---- Adam(small) on side B, beside the table work ----
   FIT_RC(fork(sB, f->ev[7]));
   const int nv = f->n_small / 4;
-  fit_adam_small_kernel<<<(nv + 255) / 256, 256, 0, sB>>>(
-      (float4*)f->sp, (float4*)f->sm, (float4*)f->sv, (float4*)f->sg, f->wsplit, nv, f->G.off / 4,
-      (f->G.off + r8(f->G.rows * f->G.cols)) / 4, f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res, f->step_base,
-      step_off, f->freeze_step, f->wd);
+  DVT_CUDA_OK(launch_k(pdl, fit_adam_small_kernel, dim3((nv + 255) / 256), dim3(256), 0, sB, (float4*)f->sp, (float4*)f->sm,
+                       (float4*)f->sv, (float4*)f->sg, nv, f->G.off / 4, (f->G.off + r8(f->G.rows * f->G.cols)) / 4,
+                       f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res, f->step_base, step_off, f->freeze_step, f->wd));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   if (!pipe) {
@@ -1219,11 +1198,11 @@ static int fit_query_reserve(Fit* f, int n) {
   if (n <= f->q_cap) return DVT_OK;
   cudaFree(f->q_enc); cudaFree(f->q_h1); cudaFree(f->q_raw); cudaFree(f->q_r1); cudaFree(f->q_r2);
   f->q_enc = f->q_h1 = f->q_raw = f->q_r1 = f->q_r2 = nullptr; f->q_cap = 0;
-  DVT_CUDA_OK(cudaMalloc(&f->q_enc, (size_t)n * f->ld_enc * 8));
-  DVT_CUDA_OK(cudaMalloc(&f->q_h1, (size_t)n * f->ld_h1 * 8));
-  DVT_CUDA_OK(cudaMalloc(&f->q_raw, (size_t)n * f->ld_raw * 8));
-  DVT_CUDA_OK(cudaMalloc(&f->q_r1, (size_t)n * f->ld_r * 8));
-  DVT_CUDA_OK(cudaMalloc(&f->q_r2, (size_t)n * f->ld_r * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_enc, (size_t)n * f->ld_enc * 4));
+  DVT_CUDA_OK(cudaMalloc(&f->q_h1, (size_t)n * f->ld_h1 * 4));
+  DVT_CUDA_OK(cudaMalloc(&f->q_raw, (size_t)n * f->ld_raw * 4));
+  DVT_CUDA_OK(cudaMalloc(&f->q_r1, (size_t)n * f->ld_r * 4));
+  DVT_CUDA_OK(cudaMalloc(&f->q_r2, (size_t)n * f->ld_r * 4));
   f->q_cap = n;
   return DVT_OK;
 }
@@ -1233,16 +1212,15 @@ int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, i
   DVT_REQUIRE(coords && out && n > 0, "fit_query: bad arguments");
   FIT_RC(fit_query_reserve(f, n));
   const int C = f->C, H1 = C / 2;
-  const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};
   fit_encode_kernel<<<(n * f->grid.n_levels * 4 + 255) / 256, 256, 0, st>>>(
-      f->grid, f->tb, f->tb.p[f->cur_host & 1], coords, sr, n, f->q_enc, f->ld_enc, cap * f->ld_enc, nullptr, 0.f, 0);
+      f->grid, f->tb, f->tb.p[f->cur_host & 1], coords, sr, n, f->q_enc, f->ld_enc, nullptr, 0.f, 0);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  FIT_RC(fit_linear(Op{f->q_enc, f->ld_enc, cap * f->ld_enc}, n, f->Lf, Op{f->wsplit + f->W1.off, f->Lf, wp}, H1,
-                    f->sp + f->b1.off, ACT_RELU, f->q_h1, f->ld_h1, cap * f->ld_h1, true, st, impl));
-  FIT_RC(fit_linear(Op{f->q_h1, f->ld_h1, cap * f->ld_h1}, n, H1, Op{f->wsplit + f->W2.off, H1, wp}, C, f->sp + f->b2.off,
-                    ACT_NONE, out, C, 0, false, st, impl));
+  FIT_RC(fit_linear(Op{f->q_enc, f->ld_enc}, n, f->Lf, Op{f->sp + f->W1.off, f->Lf}, H1, f->sp + f->b1.off, ACT_RELU,
+                    f->q_h1, f->ld_h1, st, impl));
+  FIT_RC(fit_linear(Op{f->q_h1, f->ld_h1}, n, H1, Op{f->sp + f->W2.off, H1}, C, f->sp + f->b2.off, ACT_NONE, out, C, st,
+                    impl));
   return DVT_OK;
 }
 
@@ -1251,17 +1229,16 @@ int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, i
   DVT_REQUIRE(raw && out && n > 0, "fit_residual: bad arguments");
   FIT_RC(fit_query_reserve(f, n));
   const int C = f->C, Hr = C / 4;
-  const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};
-  fit_gather_rows_kernel<<<n, 192, 0, st>>>(raw, C, sr, n, f->q_raw, f->ld_raw, cap * f->ld_raw);
+  fit_gather_rows_kernel<<<n, 192, 0, st>>>(raw, C, sr, n, f->q_raw, f->ld_raw);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  FIT_RC(fit_linear(Op{f->q_raw, f->ld_raw, cap * f->ld_raw}, n, C, Op{f->wsplit + f->R1.off, C, wp}, Hr, f->sp + f->rb1.off,
-                    ACT_RELU, f->q_r1, f->ld_r, cap * f->ld_r, true, st, impl));
-  FIT_RC(fit_linear(Op{f->q_r1, f->ld_r, cap * f->ld_r}, n, Hr, Op{f->wsplit + f->R2.off, Hr, wp}, Hr, f->sp + f->rb2.off,
-                    ACT_RELU, f->q_r2, f->ld_r, cap * f->ld_r, true, st, impl));
-  FIT_RC(fit_linear(Op{f->q_r2, f->ld_r, cap * f->ld_r}, n, Hr, Op{f->wsplit + f->R3.off, Hr, wp}, C, f->sp + f->rb3.off,
-                    ACT_NONE, out, C, 0, false, st, impl));
+  FIT_RC(fit_linear(Op{f->q_raw, f->ld_raw}, n, C, Op{f->sp + f->R1.off, C}, Hr, f->sp + f->rb1.off, ACT_RELU, f->q_r1,
+                    f->ld_r, st, impl));
+  FIT_RC(fit_linear(Op{f->q_r1, f->ld_r}, n, Hr, Op{f->sp + f->R2.off, Hr}, Hr, f->sp + f->rb2.off, ACT_RELU, f->q_r2,
+                    f->ld_r, st, impl));
+  FIT_RC(fit_linear(Op{f->q_r2, f->ld_r}, n, Hr, Op{f->sp + f->R3.off, Hr}, C, f->sp + f->rb3.off, ACT_NONE, out, C, st,
+                    impl));
   return DVT_OK;
 }
 
