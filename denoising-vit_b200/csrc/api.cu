@@ -181,8 +181,8 @@ int dvt_debug_set_timestamp_buffer(unsigned long long* dev_buf16) {
   return DVT_OK;
 }
 
-int dvt_gemm_f32x3(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K, float* out,
-                   int ldo, int splits, float* last_col_out, void* stream) {
+int dvt_gemm_f32x3(const float* A, int lda, size_t plane_a, int a_mn, const float* B, int ldb, size_t plane_b, int b_mn,
+                   int M, int N, int K, float* out, int ldo, int splits, float* last_col_out, void* stream) {
   DVT_REQUIRE(A && B && out, "dvt_gemm_f32x3: null pointer");
   GemmEpi e;
   e.debug_ts = g_debug_ts;
@@ -195,7 +195,7 @@ int dvt_gemm_f32x3(const float* A, int lda, int a_mn, const float* B, int ldb, i
     e.out_mode = OUT_F32;
   }
   GemmShape s{M, N, K, splits < 1 ? 1 : splits};
-  s.a_mn = a_mn; s.b_mn = b_mn; s.x3 = 1;
+  s.a_mn = a_mn; s.b_mn = b_mn; s.x3 = 1; s.plane_a = plane_a; s.plane_b = plane_b;
   return launch_gemm_tn(A, lda, B, ldb, TMAP_F32, s, e, reinterpret_cast<cudaStream_t>(stream), eff_impl());
 }
 

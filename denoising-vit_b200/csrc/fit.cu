@@ -12,13 +12,12 @@
 //   GEMM  dh1 = (dpred W2) * relu'        GEMM  dW2|db2 += dpred^T [h1|1]   GEMM dW1|db1 += dh1^T [enc|1]
 //   GEMM  denc = dh1 W1                   grid backward (vector atomics into the dense table gradient)
 //   [+ residual MLP backward, 5 GEMMs]    Adam(table) dense sweep           Adam(small params) + bf16 mirrors
-// All GEMMs run on tcgen05 (gemm.cu) as 3xTF32 products (fp32-accurate: bf16 operands cannot hold the cosine >= 0.999
-// parity bar; the kernel splits the fp32 operand tiles into TF32 hi / lo parts in shared memory, so
-// activations and weights exist once, as plain fp32); weight-gradient GEMMs read the activations as MN-major
+// All GEMMs run on tcgen05 (gemm.cu) as 3xTF32 products of fp32 hi/lo planes (fp32-accurate: bf16 operands cannot
+// hold the cosine >= 0.999 parity bar); weight-gradient GEMMs read the activations as MN-major
 // operands, so no transposed copies exist; bias gradients come from a ones column appended to the activation buffers.
 //
 // HBM layout: table p/m/v/g as four fp32 arrays of n_entries*8; "small" params (field MLP, G as [h*w, C],
-// residual MLP) in one flat fp32 buffer with identically laid out m / v / grad buffers.
+// residual MLP) in one flat fp32 buffer with identically laid out m / v / grad buffers and TF32 hi/lo operand planes.
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -147,7 +146,7 @@ __device__ __forceinline__ void adam8(float4& pa, float4& pb, float4& ma, float4
 // the encoded step is s, the state that is read is S_{s - npeek}.  table_fixed != nullptr: read that table (query mode).
 __global__ void __launch_bounds__(256)
 fit_encode_kernel(GridLevels g, TableBufs tb, const float* __restrict__ table_fixed, const float* __restrict__ coords,
-                  StepRows sr, int n, float* __restrict__ enc, int ld_enc,
+                  StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane,
                   const AdamScalars* __restrict__ sc, float wd, int npeek) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int q = t >> 2, k = t & 3;
@@ -200,11 +199,16 @@ fit_encode_kernel(GridLevels g, TableBufs tb, const float* __restrict__ table_fi
     acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 1);
     acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], 2);
   }
-  // lanes 0 / 1 of the quad store features 0-3 / 4-7
-  if (k < 2) {
-    float* dst = enc + (size_t)i * ld_enc + l * FIT_F + k * 4;
-    *reinterpret_cast<float4*>(dst) = k ? make_float4(acc[4], acc[5], acc[6], acc[7]) : make_float4(acc[0], acc[1], acc[2], acc[3]);
+  // lane k stores one float4: k = 0/1 the hi plane (features 0-3 / 4-7), k = 2/3 the lo plane
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = (k & 1) ? acc[4 + j] : acc[j];
+    const float hi = tf32_hi(a);
+    o[j] = (k & 2) ? a - hi : hi;
   }
+  float* dst = enc + (size_t)i * ld_enc + l * FIT_F + (k & 1) * 4 + ((k & 2) ? plane : 0);
+  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // fp32 encode (unit-test entry point: bit-level check of indices / weights against the oracle)
@@ -273,16 +277,20 @@ __global__ void fit_grid_bwd_kernel(GridLevels g, const float* __restrict__ coor
   }
 }
 
-// gather bank rows (fp32) -> [n, ld] (loss target; input of the residual MLP)
+// gather bank rows (fp32) -> hi/lo planes [n, ld] (input of the residual MLP)
 __global__ void fit_gather_rows_kernel(const float* __restrict__ bank, int C, StepRows sr, int n,
-                                       float* __restrict__ out, int ld) {
+                                       float* __restrict__ out, int ld, size_t plane) {
   pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
   pdl_trigger();
   const int i = blockIdx.x;
   const int* rows = sr.rows(n);
   const float4* src = reinterpret_cast<const float4*>(sr.bank(bank) + (size_t)(rows ? rows[i] : i) * C);
   for (int c4 = threadIdx.x; c4 < C / 4; c4 += blockDim.x) {
-    *reinterpret_cast<float4*>(out + (size_t)i * ld + c4 * 4) = __ldg(src + c4);
+    const float4 v = __ldg(src + c4);
+    const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    float* dst = out + (size_t)i * ld + c4 * 4;
+    *reinterpret_cast<float4*>(dst) = hi;
+    *reinterpret_cast<float4*>(dst + plane) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
   }
 }
 
@@ -291,15 +299,17 @@ __global__ void fit_gather_rows_kernel(const float* __restrict__ bank, int C, St
 // losses[5] (this step's slots) accumulates: total, patch_l2, cosine, residual, residual_sparsity.
 // ----------------------------------------------------------------------------------------------------
 struct LossArgs {
-  const float* raw;         // [n, ld_raw] raw ViT features of the sampled rows (gathered on a side stream: random 3 KB
-                            //  rows of a 3 GB bank are TLB misses that must not sit on the critical path)
+  const float* raw;         // [2 planes][n, ld_raw] raw ViT features of the sampled rows (hi / lo, gathered on a side stream:
+                            //  random 3 KB rows of a 3 GB bank are TLB misses that must not sit on the critical path)
   int ld_raw;
+  size_t raw_plane;
   StepRows sr;              // bank rows of this step
   const float* F;           // [n, C] field output
   const float* G;           // [hw, C] shared artifact map (fp32 master)
   const float* R;           // [n, C] residual prediction or nullptr (phase 1)
-  float* dpred;             // [n, C]
-  float* dR;                // [n, C] or nullptr
+  float* dpred;             // [2 planes][n, C] (hi / lo)
+  float* dR;                // [2 planes][n, C] or nullptr
+  size_t plane;             // n * C
   float* gG;                // [hw, C] gradient accumulator or nullptr (G frozen)
   float* losses;            // [num_iters, 5]; this step's slots are used
   int n, C, hw;
@@ -320,13 +330,14 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
   float* losses = a.losses + (size_t)a.sr.step() * 5;
   const int cell = br % a.hw;  // exact (r, c) of the patch inside its view: the "shared artifact coordinate"
   const float4* raw4 = reinterpret_cast<const float4*>(a.raw + (size_t)row * a.ld_raw);
+  const float4* raw4lo = reinterpret_cast<const float4*>(a.raw + a.raw_plane + (size_t)row * a.ld_raw);
   const float4* F4 = reinterpret_cast<const float4*>(a.F + (size_t)row * C);
   const float4* G4 = reinterpret_cast<const float4*>(a.G + (size_t)cell * C);
   const float4* R4 = HAS_R ? reinterpret_cast<const float4*>(a.R + (size_t)row * C) : nullptr;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 pred[NV], raw[NV], rp[HAS_R ? NV : 1];
   {
-    float4 f[NV], gg[NV];
+    float4 f[NV], gg[NV], rl[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {  // loads only
       const int v = lane + 32 * i;
@@ -334,10 +345,12 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       f[i] = ok ? F4[v] : z4;
       gg[i] = ok ? __ldg(G4 + v) : z4;
       raw[i] = ok ? raw4[v] : z4;
+      rl[i] = ok ? raw4lo[v] : z4;
       if (HAS_R) rp[i] = ok ? R4[v] : z4;
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
+      raw[i] = make_float4(raw[i].x + rl[i].x, raw[i].y + rl[i].y, raw[i].z + rl[i].z, raw[i].w + rl[i].w);  // hi + lo == raw
       pred[i] = make_float4(f[i].x + gg[i].x, f[i].y + gg[i].y, f[i].z + gg[i].z, f[i].w + gg[i].w);
       if (HAS_R) { pred[i].x += rp[i].x; pred[i].y += rp[i].y; pred[i].z += rp[i].z; pred[i].w += rp[i].w; }
     }
@@ -377,7 +390,12 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
     d.y = k_mse * (p.y - r.y) + k_cr * r.y + k_cp * p.y;
     d.z = k_mse * (p.z - r.z) + k_cr * r.z + k_cp * p.z;
     d.w = k_mse * (p.w - r.w) + k_cr * r.w + k_cp * p.w;
-    *reinterpret_cast<float4*>(a.dpred + (size_t)row * C + v * 4) = d;
+    {
+      const float4 hi = make_float4(tf32_hi(d.x), tf32_hi(d.y), tf32_hi(d.z), tf32_hi(d.w));
+      float* dp = a.dpred + (size_t)row * C + v * 4;
+      *reinterpret_cast<float4*>(dp) = hi;
+      *reinterpret_cast<float4*>(dp + a.plane) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
+    }
     if (a.gG) {
       float* dst = a.gG + (size_t)cell * C + v * 4;
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
@@ -393,7 +411,10 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       auto sgn = [](float x) { return (float)((x > 0.f) - (x < 0.f)); };
       const float4 dr = make_float4(k1 * ex + k2 * sgn(q.x), k1 * ey + k2 * sgn(q.y), k1 * ez + k2 * sgn(q.z),
                                     k1 * ew + k2 * sgn(q.w));
-      *reinterpret_cast<float4*>(a.dR + (size_t)row * C + v * 4) = dr;
+      const float4 hi = make_float4(tf32_hi(dr.x), tf32_hi(dr.y), tf32_hi(dr.z), tf32_hi(dr.w));
+      float* dp = a.dR + (size_t)row * C + v * 4;
+      *reinterpret_cast<float4*>(dp) = hi;
+      *reinterpret_cast<float4*>(dp + a.plane) = make_float4(dr.x - hi.x, dr.y - hi.y, dr.z - hi.z, dr.w - hi.w);
     }
   }
   if (HAS_R) {
@@ -527,7 +548,7 @@ fit_adam_table_kernel(TableBufs tb, size_t nvec, const AdamScalars* __restrict__
 
 // small params: one flat buffer; [g_lo, g_hi) is G, [r_lo, r_hi) the residual MLP, the rest the field MLP.
 __global__ void fit_adam_small_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
-                                      float4* __restrict__ g, int nvec, int g_lo,
+                                      float4* __restrict__ g, float* __restrict__ wsplit, int nvec, int g_lo,
                                       int g_hi, int r_lo, int r_hi, const AdamScalars* __restrict__ sc_main,
                                       const AdamScalars* __restrict__ sc_res, const int* __restrict__ step_base,
                                       int step_off, int freeze_step, float wd) {
@@ -547,6 +568,12 @@ __global__ void fit_adam_small_kernel(float4* __restrict__ p, float4* __restrict
     adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.inv_bc2_sqrt);
     p[i] = pp; m[i] = mm; v[i] = vv;
     g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!is_g) {  // GEMM operand planes of the weights
+      const float4 hi = make_float4(tf32_hi(pp.x), tf32_hi(pp.y), tf32_hi(pp.z), tf32_hi(pp.w));
+      *reinterpret_cast<float4*>(wsplit + (size_t)i * 4) = hi;
+      *reinterpret_cast<float4*>(wsplit + (size_t)(nvec + i) * 4) =
+          make_float4(pp.x - hi.x, pp.y - hi.y, pp.z - hi.z, pp.w - hi.w);
+    }
   }
 }
 
@@ -566,6 +593,13 @@ __global__ void fit_transpose_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
+__global__ void fit_split_kernel(const float* __restrict__ p, float* __restrict__ wsplit, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float v = p[e], hi = tf32_hi(v);
+    wsplit[e] = hi;
+    wsplit[n + e] = v - hi;
+  }
+}
 
 __global__ void fit_coord_range_kernel(const float* __restrict__ coords, size_t n2, int* __restrict__ bad) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (size_t)gridDim.x * blockDim.x) {
@@ -596,11 +630,12 @@ struct Fit {
   cudaEvent_t ev_sweep[3] = {};                // completion of the sweep launched at epoch step i (slot i % 3)
   int epoch_steps = 0;                         // pipelined steps enqueued since the sweeps were last joined
   bool enc_ready = false;                      // f->enc already holds the encoding of the next step
-  bool pdl = false;                            // programmatic dependent launch along the kernel chains of a step
+  bool pdl = true;                             // programmatic dependent launch along the kernel chains of a step
   bool pipe[2] = {true, true};                 // software-pipelined table sweep in phase 1 / 2 (see fit_enqueue_step)
   int sweep_ctas[2] = {0, 0};                  // persistent sweep CTAs in phase 1 / 2 (0 = many small CTAs)
   float *sp = nullptr, *sm = nullptr, *sv = nullptr, *sg = nullptr;
-  // activations (plain fp32; the x3 GEMMs split them on the fly)
+  float* wsplit = nullptr;  // [2][n_small] TF32 hi / lo planes of the small params (x3 GEMM operands)
+  // activations: GEMM operands are stored as two fp32 planes (hi, lo), plane stride = bsz * ld
   float *enc = nullptr, *h1 = nullptr, *dpred = nullptr, *dh1 = nullptr;
   float *Fout = nullptr, *denc = nullptr;
   float *rawb = nullptr, *r1 = nullptr, *r2 = nullptr, *dR = nullptr, *dr2 = nullptr, *dr1 = nullptr;
@@ -624,9 +659,9 @@ struct Fit {
   int graph_steps = 0;
   long long graph1_nodes = 0, graph2_nodes = 0;
   cudaStream_t stream = nullptr;      // main stream of a step (critical path)
-  cudaStream_t sB = nullptr, sC = nullptr;  // side streams: independent GEMM chains run concurrently with the main one
+  cudaStream_t sB = nullptr, sC = nullptr, sE = nullptr;  // side streams: independent GEMM chains beside the main one
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  cudaEvent_t ev[12] = {};
+  cudaEvent_t ev[16] = {};
   // query workspace
   int q_cap = 0;
   float *q_enc = nullptr, *q_h1 = nullptr, *q_raw = nullptr, *q_r1 = nullptr, *q_r2 = nullptr;
@@ -660,6 +695,7 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->stream, cudaStreamNonBlocking, prio_hi));
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sB, cudaStreamNonBlocking, prio_hi));
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sC, cudaStreamNonBlocking, prio_hi));
+  DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sE, cudaStreamNonBlocking, prio_hi));
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sD, cudaStreamNonBlocking, prio_lo));  // the sweep yields to the chain
   for (auto& e : f->ev) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : f->ev_sweep) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -670,15 +706,15 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
     //   DVT_FIT_SWEEP_CTAS="a[,b]"  per phase (1 [, 2]): n > 0 pipelined sweep on n persistent CTAs (1024 threads, one
     //                               per SM); 0 pipelined sweep on 8 x #SM CTAs of 256 threads; -1 sequential schedule
     //   DVT_FIT_PIPELINE=0          sequential schedule in both phases
-    int cfg[2] = {40, -1};
+    int cfg[2] = {40, 40};
     if (const char* se = getenv("DVT_FIT_SWEEP_CTAS")) {
       int a = 0, b = 0;
       const int got = sscanf(se, "%d,%d", &a, &b);
       if (got >= 1) { cfg[0] = a; cfg[1] = got >= 2 ? b : a; }
     }
-    //   DVT_FIT_PDL=1               programmatic dependent launch along the kernel chains of a step
+    //   DVT_FIT_PDL=0               plain stream-ordered launches (no programmatic dependent launch)
     const char* pd = getenv("DVT_FIT_PDL");
-    f->pdl = pd && pd[0] == '1';  // opt-in until validated on the GPU
+    f->pdl = !(pd && pd[0] == '0');
     const char* pe = getenv("DVT_FIT_PIPELINE");
     const bool off = pe && pe[0] == '0';
     for (int q = 0; q < 2; ++q) {
@@ -711,12 +747,12 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
     A((void**)&f->tb.g[q], f->n_table * 4); A((void**)&f->tb.stamp[q], f->n_table / FIT_F * 4);
   }
   A((void**)&f->sp, (size_t)off * 4); A((void**)&f->sm, (size_t)off * 4); A((void**)&f->sv, (size_t)off * 4);
-  A((void**)&f->sg, (size_t)off * 4);
+  A((void**)&f->sg, (size_t)off * 4); A((void**)&f->wsplit, (size_t)off * 8);
   const size_t n = bsz;
-  A((void**)&f->enc, n * f->ld_enc * 4); A((void**)&f->h1, n * f->ld_h1 * 4); A((void**)&f->dpred, n * C * 4);
-  A((void**)&f->dh1, n * H1 * 4); A((void**)&f->Fout, n * C * 4); A((void**)&f->denc, n * f->Lf * 4);
-  A((void**)&f->rawb, n * f->ld_raw * 4); A((void**)&f->r1, n * f->ld_r * 4); A((void**)&f->r2, n * f->ld_r * 4);
-  A((void**)&f->dR, n * C * 4); A((void**)&f->dr2, n * Hr * 4); A((void**)&f->dr1, n * Hr * 4);
+  A((void**)&f->enc, n * f->ld_enc * 8); A((void**)&f->h1, n * f->ld_h1 * 8); A((void**)&f->dpred, n * C * 8);
+  A((void**)&f->dh1, n * H1 * 8); A((void**)&f->Fout, n * C * 4); A((void**)&f->denc, n * f->Lf * 4);
+  A((void**)&f->rawb, n * f->ld_raw * 8); A((void**)&f->r1, n * f->ld_r * 8); A((void**)&f->r2, n * f->ld_r * 8);
+  A((void**)&f->dR, n * C * 8); A((void**)&f->dr2, n * Hr * 8); A((void**)&f->dr1, n * Hr * 8);
   A((void**)&f->Rout, n * C * 4); A((void**)&f->step_base, sizeof(int));
   A((void**)&f->inputs_dev, sizeof(FitInputs));
   if (rc) { for (void* p : f->owned) cudaFree(p); delete f; return rc; }
@@ -744,6 +780,7 @@ void fit_destroy(Fit* f) {
   if (f->stream) cudaStreamDestroy(f->stream);
   if (f->sB) cudaStreamDestroy(f->sB);
   if (f->sC) cudaStreamDestroy(f->sC);
+  if (f->sE) cudaStreamDestroy(f->sE);
   if (f->sD) cudaStreamDestroy(f->sD);
   for (auto& e : f->ev) if (e) cudaEventDestroy(e);
   for (auto& e : f->ev_sweep) if (e) cudaEventDestroy(e);
@@ -899,37 +936,40 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   f->epoch_steps = 0;
   DVT_CUDA_OK(cudaMemset(f->sm, 0, (size_t)f->n_small * 4)); DVT_CUDA_OK(cudaMemset(f->sv, 0, (size_t)f->n_small * 4));
   DVT_CUDA_OK(cudaMemset(f->sg, 0, (size_t)f->n_small * 4));
+  fit_split_kernel<<<256, 256>>>(f->sp, f->wsplit, (size_t)f->n_small);
+  DVT_CUDA_OK(cudaGetLastError());
   DVT_CUDA_OK(cudaDeviceSynchronize());
   return DVT_OK;
 }
 
 #define FIT_RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
-// GEMM operands of the fit are plain fp32 matrices; all products are 3xTF32 (fp32-accurate, gemm.cu "x3").
+// GEMM operands of the fit are fp32 hi/lo plane pairs; all products are 3xTF32 (fp32-accurate, gemm.cu "x3").
 struct Op {
   const float* p;
   int ld;
+  size_t plane;
 };
 
-// Y = act(X W^T + b):  X [M, K], W [N, K]
-static int fit_linear(Op X, int M, int K, Op W, int N, const float* bias, int act, float* out, int ldo, cudaStream_t st,
-                      int impl, bool pdl = false) {
+// Y = act(X W^T + b):  X [M, K] planes, W [N, K] planes.  split_out: Y is written as hi/lo planes (feeds a GEMM).
+static int fit_linear(Op X, int M, int K, Op W, int N, const float* bias, int act, float* out, int ldo, size_t out_plane,
+                      bool split_out, cudaStream_t st, int impl, bool pdl = false) {
   GemmEpi e;
-  e.bias = bias; e.act = act; e.out = out; e.ldo = ldo;
-  e.out_mode = OUT_F32;
+  e.bias = bias; e.act = act; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
+  e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
   GemmShape s{M, N, K, 1};
-  s.x3 = 1; s.pdl = pdl;
+  s.x3 = 1; s.plane_a = X.plane; s.plane_b = W.plane; s.pdl = pdl;
   return launch_gemm_tn(X.p, X.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
 // dX = (dY . W) * (H > 0):  dY [M, Nout] K-major A; W stored [Nout, Kin] = MN-major B with N = Kin
 static int fit_dgrad(Op dY, int M, int Nout, Op W, int Kin, const float* Hmask, int ldmask, float* out, int ldo,
-                     cudaStream_t st, int impl, bool pdl = false) {
+                     size_t out_plane, bool split_out, cudaStream_t st, int impl, bool pdl = false) {
   GemmEpi e;
-  e.mask_f32 = Hmask; e.ldmask = ldmask; e.out = out; e.ldo = ldo;
-  e.out_mode = OUT_F32;
+  e.mask_f32 = Hmask; e.ldmask = ldmask; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
+  e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
   GemmShape s{M, Kin, Nout, 1};
-  s.b_mn = 1; s.x3 = 1; s.pdl = pdl;
+  s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = W.plane; s.pdl = pdl;
   return launch_gemm_tn(dY.p, dY.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
@@ -943,7 +983,7 @@ static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb
   const int tiles = ((Nout + 127) / 128) * ((Kin + 1 + 63) / 64);
   int splits = std::max(1, std::min(num_sms() / std::max(tiles, 1), kb / 4));
   GemmShape s{Nout, Kin + 1, n, splits};
-  s.a_mn = 1; s.b_mn = 1; s.x3 = 1; s.pdl = pdl;
+  s.a_mn = 1; s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = X.plane; s.pdl = pdl;
   return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
 }
 
@@ -972,7 +1012,7 @@ static int fit_enqueue_encode(Fit* f, int step_off, int npeek, cudaStream_t st) 
   const StepRows sr{f->idx, f->step_base, step_off, f->inputs_dev};
   const int tb = 256, blocks = (n * f->grid.n_levels * 4 + tb - 1) / tb;
   DVT_CUDA_OK(launch_k(f->pdl, fit_encode_kernel, dim3(blocks), dim3(tb), 0, st, f->grid, f->tb, nullptr, f->coords, sr, n,
-                       f->enc, f->ld_enc, f->sc_main, f->wd, npeek));
+                       f->enc, f->ld_enc, (size_t)n * f->ld_enc, f->sc_main, f->wd, npeek));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;
@@ -996,11 +1036,14 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   const int tb = 256;
   const int enc_blocks = (n * f->grid.n_levels + tb - 1) / tb;
   float* sp = f->sp; float* sg = f->sg;
-  auto W = [&](const Seg& sgm) { return Op{f->sp + sgm.off, sgm.cols}; };  // weights: the fp32 masters themselves
-  const Op enc{f->enc, f->ld_enc}, h1{f->h1, f->ld_h1}, dpred{f->dpred, C}, dh1{f->dh1, H1};
-  const Op rawb{f->rawb, f->ld_raw}, r1{f->r1, f->ld_r}, r2{f->r2, f->ld_r};
-  const Op dR{f->dR, C}, dr2{f->dr2, Hr}, dr1{f->dr1, Hr};
-  cudaStream_t sB = f->sB, sC = f->sC, sD = f->sD;
+  const size_t wp = (size_t)f->n_small;  // weight plane stride
+  auto W = [&](const Seg& sgm) { return Op{f->wsplit + sgm.off, sgm.cols, wp}; };
+  const size_t p_enc = (size_t)n * f->ld_enc, p_h1 = (size_t)n * f->ld_h1, p_nc = (size_t)n * C, p_nh = (size_t)n * H1;
+  const size_t p_raw = (size_t)n * f->ld_raw, p_r = (size_t)n * f->ld_r, p_nr = (size_t)n * Hr;
+  const Op enc{f->enc, f->ld_enc, p_enc}, h1{f->h1, f->ld_h1, p_h1}, dpred{f->dpred, C, p_nc}, dh1{f->dh1, H1, p_nh};
+  const Op rawb{f->rawb, f->ld_raw, p_raw}, r1{f->r1, f->ld_r, p_r}, r2{f->r2, f->ld_r, p_r};
+  const Op dR{f->dR, C, p_nc}, dr2{f->dr2, Hr, p_nr}, dr1{f->dr1, Hr, p_nr};
+  cudaStream_t sB = f->sB, sC = f->sC, sD = f->sD, sE = f->sE;
   const bool pdl = f->pdl;
   auto fork = [&](cudaStream_t to, cudaEvent_t e) -> int {
     DVT_CUDA_OK(cudaEventRecord(e, st));
@@ -1014,33 +1057,36 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   };
   // ---- forward ----
   FIT_RC(fork(sB, f->ev[0]));  // side B: gather the sampled bank rows (+ residual MLP forward in phase 2)
-  DVT_CUDA_OK(launch_k(pdl, fit_gather_rows_kernel, dim3(n), dim3(192), 0, sB, f->bank, C, sr, n, f->rawb, f->ld_raw));
+  DVT_CUDA_OK(launch_k(pdl, fit_gather_rows_kernel, dim3(n), dim3(192), 0, sB, f->bank, C, sr, n, f->rawb, f->ld_raw, p_raw));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   const bool pipe = f->pipe[phase2 ? 1 : 0];
   if (!pipe) FIT_RC(fit_enqueue_encode(f, step_off, 0, st));  // else f->enc is already this step's (fit_run)
   if (phase2) {
-    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, sB, impl, pdl));
-    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, sB, impl, pdl));
-    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, sB, impl, pdl));
+    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl, pdl));
+    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl, pdl));
+    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl, pdl));
   }
-  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, st, impl, pdl));
-  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, st, impl, pdl));
+  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl, pdl));
+  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl, pdl));
   FIT_RC(join(sB, f->ev[1]));
   // ---- loss + d pred ----
   LossArgs la;
-  la.raw = f->rawb; la.ld_raw = f->ld_raw; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
-  la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.gG = phase2 ? nullptr : sg + f->G.off;
+  la.raw = f->rawb; la.ld_raw = f->ld_raw; la.raw_plane = p_raw; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
+  la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.plane = p_nc; la.gG = phase2 ? nullptr : sg + f->G.off;
   la.losses = f->losses; la.n = n; la.C = C; la.hw = f->hw; la.loss_scale = f->loss_scale;
   FIT_RC(launch_loss(la, st, pdl));
   // ---- backward ----
   FIT_RC(fork(sB, f->ev[2]));
-  if (phase2) FIT_RC(fork(sC, f->ev[3]));
+  if (phase2) {
+    FIT_RC(fork(sC, f->ev[3]));
+    FIT_RC(fork(sE, f->ev[11]));
+  }
   FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl, pdl));          // side B
-  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, st, impl, pdl));  // main
+  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl, pdl));  // main
   FIT_RC(fork(sB, f->ev[4]));  // dh1 ready
   FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl, pdl));           // side B (reads enc)
-  FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, st, impl, pdl));
+  FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl, pdl));
   // the gradient ring slot of this step was re-zeroed by the sweep of step t-2, which also produced the state the
   // next encode reads
   if (pipe && f->epoch_steps >= 2)
@@ -1049,21 +1095,27 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
                        f->tb));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  if (phase2) {                                                                              // side C
-    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, sC, impl, pdl));
-    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sC, impl, pdl));
-    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, sC, impl, pdl));
-    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sC, impl, pdl));
+  if (phase2) {
+    // residual MLP backward: the data-gradient chain on side C, the weight-gradient GEMMs that do not feed it on side E
+    //   side C: dr2 = dR.R3 -> dr1 = dr2.R2 -> dR1      side E: dR3 (needs dR, r2 only) -> [dr2 ready] dR2
+    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, sC, impl, pdl));
+    DVT_CUDA_OK(cudaEventRecord(f->ev[12], sC));                                              // dr2 ready
+    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, sC, impl, pdl));
     FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl, pdl));
+    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sE, impl, pdl));
+    DVT_CUDA_OK(cudaStreamWaitEvent(sE, f->ev[12], 0));
+    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sE, impl, pdl));
     FIT_RC(join(sC, f->ev[5]));
+    FIT_RC(join(sE, f->ev[13]));
   }
   FIT_RC(join(sB, f->ev[6]));  // all small-parameter gradients complete; enc no longer read by a wgrad
   // ---- Adam(small) on side B, beside the table work ----
   FIT_RC(fork(sB, f->ev[7]));
   const int nv = f->n_small / 4;
   DVT_CUDA_OK(launch_k(pdl, fit_adam_small_kernel, dim3((nv + 255) / 256), dim3(256), 0, sB, (float4*)f->sp, (float4*)f->sm,
-                       (float4*)f->sv, (float4*)f->sg, nv, f->G.off / 4, (f->G.off + r8(f->G.rows * f->G.cols)) / 4,
-                       f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res, f->step_base, step_off, f->freeze_step, f->wd));
+                       (float4*)f->sv, (float4*)f->sg, f->wsplit, nv, f->G.off / 4,
+                       (f->G.off + r8(f->G.rows * f->G.cols)) / 4, f->R1.off / 4, f->n_small / 4, f->sc_main, f->sc_res,
+                       f->step_base, step_off, f->freeze_step, f->wd));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   if (!pipe) {
@@ -1198,11 +1250,11 @@ static int fit_query_reserve(Fit* f, int n) {
   if (n <= f->q_cap) return DVT_OK;
   cudaFree(f->q_enc); cudaFree(f->q_h1); cudaFree(f->q_raw); cudaFree(f->q_r1); cudaFree(f->q_r2);
   f->q_enc = f->q_h1 = f->q_raw = f->q_r1 = f->q_r2 = nullptr; f->q_cap = 0;
-  DVT_CUDA_OK(cudaMalloc(&f->q_enc, (size_t)n * f->ld_enc * 4));
-  DVT_CUDA_OK(cudaMalloc(&f->q_h1, (size_t)n * f->ld_h1 * 4));
-  DVT_CUDA_OK(cudaMalloc(&f->q_raw, (size_t)n * f->ld_raw * 4));
-  DVT_CUDA_OK(cudaMalloc(&f->q_r1, (size_t)n * f->ld_r * 4));
-  DVT_CUDA_OK(cudaMalloc(&f->q_r2, (size_t)n * f->ld_r * 4));
+  DVT_CUDA_OK(cudaMalloc(&f->q_enc, (size_t)n * f->ld_enc * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_h1, (size_t)n * f->ld_h1 * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_raw, (size_t)n * f->ld_raw * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_r1, (size_t)n * f->ld_r * 8));
+  DVT_CUDA_OK(cudaMalloc(&f->q_r2, (size_t)n * f->ld_r * 8));
   f->q_cap = n;
   return DVT_OK;
 }
@@ -1212,15 +1264,16 @@ int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, i
   DVT_REQUIRE(coords && out && n > 0, "fit_query: bad arguments");
   FIT_RC(fit_query_reserve(f, n));
   const int C = f->C, H1 = C / 2;
+  const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};
   fit_encode_kernel<<<(n * f->grid.n_levels * 4 + 255) / 256, 256, 0, st>>>(
-      f->grid, f->tb, f->tb.p[f->cur_host & 1], coords, sr, n, f->q_enc, f->ld_enc, nullptr, 0.f, 0);
+      f->grid, f->tb, f->tb.p[f->cur_host & 1], coords, sr, n, f->q_enc, f->ld_enc, cap * f->ld_enc, nullptr, 0.f, 0);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  FIT_RC(fit_linear(Op{f->q_enc, f->ld_enc}, n, f->Lf, Op{f->sp + f->W1.off, f->Lf}, H1, f->sp + f->b1.off, ACT_RELU,
-                    f->q_h1, f->ld_h1, st, impl));
-  FIT_RC(fit_linear(Op{f->q_h1, f->ld_h1}, n, H1, Op{f->sp + f->W2.off, H1}, C, f->sp + f->b2.off, ACT_NONE, out, C, st,
-                    impl));
+  FIT_RC(fit_linear(Op{f->q_enc, f->ld_enc, cap * f->ld_enc}, n, f->Lf, Op{f->wsplit + f->W1.off, f->Lf, wp}, H1,
+                    f->sp + f->b1.off, ACT_RELU, f->q_h1, f->ld_h1, cap * f->ld_h1, true, st, impl));
+  FIT_RC(fit_linear(Op{f->q_h1, f->ld_h1, cap * f->ld_h1}, n, H1, Op{f->wsplit + f->W2.off, H1, wp}, C, f->sp + f->b2.off,
+                    ACT_NONE, out, C, 0, false, st, impl));
   return DVT_OK;
 }
 
@@ -1229,16 +1282,17 @@ int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, i
   DVT_REQUIRE(raw && out && n > 0, "fit_residual: bad arguments");
   FIT_RC(fit_query_reserve(f, n));
   const int C = f->C, Hr = C / 4;
+  const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};
-  fit_gather_rows_kernel<<<n, 192, 0, st>>>(raw, C, sr, n, f->q_raw, f->ld_raw);
+  fit_gather_rows_kernel<<<n, 192, 0, st>>>(raw, C, sr, n, f->q_raw, f->ld_raw, cap * f->ld_raw);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
-  FIT_RC(fit_linear(Op{f->q_raw, f->ld_raw}, n, C, Op{f->sp + f->R1.off, C}, Hr, f->sp + f->rb1.off, ACT_RELU, f->q_r1,
-                    f->ld_r, st, impl));
-  FIT_RC(fit_linear(Op{f->q_r1, f->ld_r}, n, Hr, Op{f->sp + f->R2.off, Hr}, Hr, f->sp + f->rb2.off, ACT_RELU, f->q_r2,
-                    f->ld_r, st, impl));
-  FIT_RC(fit_linear(Op{f->q_r2, f->ld_r}, n, Hr, Op{f->sp + f->R3.off, Hr}, C, f->sp + f->rb3.off, ACT_NONE, out, C, st,
-                    impl));
+  FIT_RC(fit_linear(Op{f->q_raw, f->ld_raw, cap * f->ld_raw}, n, C, Op{f->wsplit + f->R1.off, C, wp}, Hr, f->sp + f->rb1.off,
+                    ACT_RELU, f->q_r1, f->ld_r, cap * f->ld_r, true, st, impl));
+  FIT_RC(fit_linear(Op{f->q_r1, f->ld_r, cap * f->ld_r}, n, Hr, Op{f->wsplit + f->R2.off, Hr, wp}, Hr, f->sp + f->rb2.off,
+                    ACT_RELU, f->q_r2, f->ld_r, cap * f->ld_r, true, st, impl));
+  FIT_RC(fit_linear(Op{f->q_r2, f->ld_r, cap * f->ld_r}, n, Hr, Op{f->wsplit + f->R3.off, Hr, wp}, C, f->sp + f->rb3.off,
+                    ACT_NONE, out, C, 0, false, st, impl));
   return DVT_OK;
 }
 

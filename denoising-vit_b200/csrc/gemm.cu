@@ -4,9 +4,7 @@
 //   warp 0      TMA producer   (A: 128 x 128B box, B: BN x 128B box, SWIZZLE_128B, 3-5 stage mbarrier ring)
 //   warp 1      MMA issuer     (lane 0 issues tcgen05.mma M=128 N=BN K=16/8; accumulators in TMEM, 2 stages)
 //   warps 2..9  epilogue       (tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> coalesced stores;
-//               two warps per TMEM lane quadrant take alternating 32-column chunks)
-//   x3 kernels only: 4 more "split" warps turn each fp32 operand tile that TMA delivered into its TF32 hi / lo parts in
-//               shared memory (hi in place, lo next to it), so HBM / L2 hold and move the fp32 operands once
+//               two warps per TMEM lane quadrant take alternating 32-column chunks; 4 warps in the x3 kernels)
 // K tails, M tails and N tails are handled by TMA zero-fill plus masking in the epilogue.
 //
 // Used for: patch-embed, QKV, attention out-proj, MLP fc1/fc2 (reference: timm VisionTransformer reached from
@@ -32,17 +30,15 @@ constexpr int SCR_PITCH = 36;  // floats; 16B-aligned rows, conflict-free for th
 template <int BN, int STAGES, bool X3 = false>
 struct GemmSmem {
   static constexpr int EW = epi_warps(BN, X3);
-  static constexpr int XW = X3 ? 4 : 0;                          // operand-split warps
-  static constexpr int THREADS = 32 * (2 + EW + XW);
-  static constexpr int A_BYTES = BM * KB_BYTES * (X3 ? 2 : 1);  // x3: hi part (where TMA writes the fp32 tile), then lo
+  static constexpr int THREADS = 32 * (2 + EW);
+  static constexpr int A_BYTES = BM * KB_BYTES * (X3 ? 2 : 1);  // x3: hi plane then lo plane
   static constexpr int B_BYTES = BN * KB_BYTES * (X3 ? 2 : 1);
-  static constexpr int A_TX = BM * KB_BYTES, B_TX = BN * KB_BYTES;  // bytes TMA delivers per stage
   static constexpr int SCR_BYTES = EW * 32 * SCR_PITCH * 4;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
   static constexpr int OFF_SCR = OFF_B + STAGES * B_BYTES;
   static constexpr int OFF_BAR = OFF_SCR + SCR_BYTES;
-  static constexpr int NUM_BARS = 3 * STAGES + 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + alignment slack
 };
@@ -62,34 +58,6 @@ __device__ __forceinline__ void epi_scalar_tail(const GemmEpi& e, const GemmShap
       const float x = scr[i * SCR_PITCH + (lane & 7) * 4 + q];
       epi_post1(e, m, n + q, epi_pre(e, m, n + q, has_k ? x : 0.0f));
     }
-  }
-}
-
-// x3 operand split of one staged tile: every 16-byte chunk x of the hi part (the fp32 data TMA wrote, swizzled) becomes
-// hi = x & 0xFFFFE000 in place and lo = x - hi at the same offset of the lo part.  The operation is element-wise, so it
-// is independent of the swizzle pattern; both parts are 1024-byte aligned, which keeps the pattern identical.
-//   K-major tile : [ROWS x 128 B] hi, lo part ROWS * 128 B further;   MN-major tile: ROWS / 32 atoms of 8192 B, each
-//   [32 k-rows x 128 B] hi followed by its lo part 4096 B further.
-template <bool MN, int ROWS, int NT>
-__device__ __forceinline__ void x3_split_tile(uint8_t* base, int tid) {
-  constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks of the hi part
-  static_assert(CHUNKS % NT == 0, "split work must divide evenly");
-  constexpr int PER = CHUNKS / NT;
-  constexpr int LO_OFF = MN ? 4096 : ROWS * 128;
-  float4 v[PER];
-  uint32_t off[PER];
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int c = tid + j * NT;
-    off[j] = MN ? (uint32_t)((c >> 8) * 8192 + (c & 255) * 16) : (uint32_t)(c * 16);
-    v[j] = *reinterpret_cast<const float4*>(base + off[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const float4 hi = make_float4(tf32_hi(v[j].x), tf32_hi(v[j].y), tf32_hi(v[j].z), tf32_hi(v[j].w));
-    *reinterpret_cast<float4*>(base + off[j]) = hi;
-    *reinterpret_cast<float4*>(base + off[j] + LO_OFF) =
-        make_float4(v[j].x - hi.x, v[j].y - hi.y, v[j].z - hi.z, v[j].w - hi.w);
   }
 }
 
@@ -118,7 +86,6 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint64_t* xfull = bars + 2 * STAGES + 4;  // x3: operand tile of the stage has been split into hi / lo
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
 
   const int warp = threadIdx.x >> 5;
@@ -145,7 +112,6 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
-      if (X3) mbar_init(&xfull[i], L::XW);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -180,10 +146,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
-          mbar_expect_tx(&full[stage], X3 ? L::A_TX + L::B_TX : L::A_BYTES + L::B_BYTES);
+          mbar_expect_tx(&full[stage], L::A_BYTES + L::B_BYTES);
           if (X3) {
-            // fp32 operands through 3-D maps (inner, rows, 1); the tile lands in the hi part of the stage (K-major) or of
-            // each 32-wide atom (MN-major); the split warps derive the lo parts
+            // fp32 hi/lo planes: 3-D maps (inner, rows, plane); one box brings both planes of a tile / atom
             if (A_MN) {
 #pragma unroll
               for (int a = 0; a < BM / 32; ++a)
@@ -238,14 +203,14 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(X3 ? &xfull[stage] : &full[stage], phase, 3);
+          mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
           if (kb == kb0) stampt(2);  // first operands landed
           // K-major: rows of 128 B (one swizzle atom of K), 8-row groups 1024 B apart; K advances 32 B per MMA.
           // MN-major (bf16): tile = [MN/64 atoms][BK k-rows][64 mn]; atoms BK*128 B apart (LBO), 8-k groups 1024 B
           // apart (SBO); K advances 16 rows = 2048 B per MMA.
-          // x3 (fp32 hi / lo parts): K-major tile = [part][rows][128 B]; MN-major tile = [MN/32 atoms][part][32 k-rows]
-          // [32 mn] (atoms 8192 B apart, lo part +4096 B, K advances 8 rows = 1024 B per MMA).  MN-major TF32 operands
+          // x3 (fp32 hi/lo planes): K-major tile = [plane][rows][128 B]; MN-major tile = [MN/32 atoms][plane][32 k-rows]
+          // [32 mn] (atoms 8192 B apart, lo plane +4096 B, K advances 8 rows = 1024 B per MMA).  MN-major TF32 operands
           // must use the "128B swizzle with 32B atoms" layout (descriptor layout type 1, TMA SWIZZLE_128B_ATOM_32B):
           // the swizzle pattern repeats every 4 K-rows, so the stride between K groups (SBO) is 512 B.
           const uint32_t a_base = smem_u32(sA + stage * L::A_BYTES), b_base = smem_u32(sB + stage * L::B_BYTES);
@@ -285,31 +250,6 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
-        }
-      }
-    }
-  } else if (X3 && warp >= 2 + L::EW) {
-    // ===================== x3 operand-split warps =====================
-    if constexpr (X3) {
-      constexpr int NT = L::XW * 32;
-      const int tid = threadIdx.x - 32 * (2 + L::EW);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int split = t % s.splits;
-        const int kb0 = split * kb_per_split;
-        const int kb1 = min(kb_total, kb0 + kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full[stage], phase, 6);
-          x3_split_tile<A_MN, BM, NT>(sA + stage * L::A_BYTES, tid);
-          x3_split_tile<B_MN, BN, NT>(sB + stage * L::B_BYTES, tid);
-          fence_async_smem();  // generic-proxy writes -> visible to the tensor core's operand reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&xfull[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
       }
     }
@@ -495,10 +435,10 @@ __global__ void gemm_tn_simt_kernel(const T* __restrict__ A, int lda, const T* _
   for (int k0 = 0; k0 < s.K; k0 += 16) {
     int ka = k0 + tx;
     const T* ap = s.a_mn ? A + (size_t)ka * lda + m : A + (size_t)m * lda + ka;
-    sa[ty][tx] = (m < s.M && ka < s.K) ? ld_as_float(ap) : 0.0f;
+    sa[ty][tx] = (m < s.M && ka < s.K) ? ld_as_float(ap) + (s.x3 ? ld_as_float(ap + s.plane_a) : 0.0f) : 0.0f;
     int nb = blockIdx.x * 16 + ty;
     const T* bp = s.b_mn ? B + (size_t)ka * ldb + nb : B + (size_t)nb * ldb + ka;
-    sb[ty][tx] = (nb < s.N && ka < s.K) ? ld_as_float(bp) : 0.0f;
+    sb[ty][tx] = (nb < s.N && ka < s.K) ? ld_as_float(bp) + (s.x3 ? ld_as_float(bp + s.plane_b) : 0.0f) : 0.0f;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
@@ -596,18 +536,15 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
   if (s.x3) {
     DVT_REQUIRE(dtype == TMAP_F32, "gemm: x3 needs fp32 operands");
     DVT_REQUIRE(!(s.a_mn && !s.b_mn), "gemm: A MN-major with B K-major is not instantiated");
-    DVT_REQUIRE((lda * 4) % 16 == 0 && (ldb * 4) % 16 == 0, "gemm: x3 pitches must be multiples of 16 bytes");
-    DVT_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-                "gemm: operands must be 16-byte aligned");
+    DVT_REQUIRE((lda * 4) % 16 == 0 && (ldb * 4) % 16 == 0 && (s.plane_a * 4) % 16 == 0 && (s.plane_b * 4) % 16 == 0,
+                "gemm: x3 pitches must be multiples of 16 bytes");
     CUtensorMap tA, tB;
     int rc3;
-    // (third dimension of extent 1: the 3-D encoder is the one that knows the 32-byte-atom swizzle of MN-major TF32)
-    const uint64_t pa = (uint64_t)lda * 4 * (uint64_t)(s.a_mn ? s.K : s.M), pb = (uint64_t)ldb * 4 * (uint64_t)(s.b_mn ? s.K : s.N);
-    if (s.a_mn) rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.M, (uint64_t)s.K, 1, (uint64_t)lda * 4, pa, 32, 32, 1, true);
-    else rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.K, (uint64_t)s.M, 1, (uint64_t)lda * 4, pa, 32, BM, 1);
+    if (s.a_mn) rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.M, (uint64_t)s.K, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, 32, 2, true);
+    else rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.K, (uint64_t)s.M, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, BM, 2);
     if (rc3) return rc3;
-    if (s.b_mn) rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.N, (uint64_t)s.K, 1, (uint64_t)ldb * 4, pb, 32, 32, 1, true);
-    else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 1, (uint64_t)ldb * 4, pb, 32, 64, 1);
+    if (s.b_mn) rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.N, (uint64_t)s.K, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 32, 2, true);
+    else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 64, 2);
     if (rc3) return rc3;
     if (s.a_mn) return launch_tc<64, 3, true, true, true, true>(tA, tB, s, epi, stream);
     if (s.b_mn) return launch_tc<64, 3, true, false, true, true>(tA, tB, s, epi, stream);

@@ -12,6 +12,7 @@ enum GemmOut {
   OUT_F32_ATOMIC = 2,  // out[m, n] += v                    (fp32 atomics; split-K partial sums)
   OUT_F32_RESID = 3,   // out[m, n] += gamma[n] * v         (fp32 residual stream, in place; gamma may be null)
   OUT_F32_REMAP = 4,   // out[remap(m), n] = v + addend[m % rows_per_group, n]   (patch-embed -> token rows)
+  OUT_F32_SPLIT = 5,   // out[m, n] = tf32_hi(v), out[out_plane + m*ldo + n] = v - tf32_hi(v)   (operand of an x3 GEMM)
 };
 
 // fp32 value -> (hi, lo) with hi exactly representable in TF32 (low 13 mantissa bits zero) and hi + lo == v exactly
@@ -29,6 +30,7 @@ struct GemmEpi {
   int out_mode = OUT_BF16;
   void* out = nullptr;
   int ldo = 0;
+  size_t out_plane = 0;               // OUT_F32_SPLIT: element offset of the lo plane
   unsigned long long* debug_ts = nullptr;  // optional [8]: globaltimer (ns) milestones of CTA 0 (profiling aid)
   int last_col_n = -1;                // = N-1 when last_col_out is set (filled in by launch_gemm)
   float* last_col_out = nullptr;      // OUT_F32_ATOMIC only: column N-1 is accumulated into last_col_out[m] instead
@@ -45,9 +47,11 @@ struct GemmShape {
   int splits;    // split-K factor (>1 requires OUT_F32_ATOMIC)
   int a_mn = 0;  // 0: A is [M, K] row-major (K contiguous);  1: A is stored as [K, M] row-major (M contiguous)
   int b_mn = 0;  // 0: B is [N, K] row-major (K contiguous);  1: B is stored as [K, N] row-major (N contiguous)
-  // 3xTF32 ("x3"): fp32-accurate product of plain fp32 operands on the tensor cores.  The kernel splits every operand
-  // tile in shared memory into hi = TF32-exact part and lo = x - hi and accumulates A_lo.B_hi + A_hi.B_lo + A_hi.B_hi.
+  // 3xTF32 ("x3"): fp32-accurate product on the tensor cores.  Each fp32 operand is stored as two planes
+  // (hi = TF32-exact part at the base pointer, lo = remainder at base + plane elements) and the kernel accumulates
+  // A_hi.B_hi + A_hi.B_lo + A_lo.B_hi.
   int x3 = 0;
+  size_t plane_a = 0, plane_b = 0;
   int pdl = 0;   // launch with programmatic stream serialisation (the kernel calls pdl_wait() after its set-up)
 };
 
@@ -97,6 +101,12 @@ __device__ __forceinline__ void epi_post1(const GemmEpi& e, int m, int n, float 
       float a = e.addend ? __ldg(e.addend + (size_t)p * e.ldo + n) : 0.0f;
       reinterpret_cast<float*>(e.out)[row * e.ldo + n] = v + a;
     } break;
+    case OUT_F32_SPLIT: {
+      float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + n;
+      const float hi = tf32_hi(v);
+      o[0] = hi;
+      o[e.out_plane] = v - hi;
+    } break;
   }
 }
 
@@ -137,6 +147,12 @@ __device__ __forceinline__ void epi_post4(const GemmEpi& e, int m, int n, float4
       v.z += a.z;
       v.w += a.w;
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + row * e.ldo + n) = v;
+    } break;
+    case OUT_F32_SPLIT: {
+      float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + n;
+      const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      *reinterpret_cast<float4*>(o) = hi;
+      *reinterpret_cast<float4*>(o + e.out_plane) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
     } break;
   }
 }

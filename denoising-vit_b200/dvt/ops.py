@@ -100,17 +100,23 @@ def gemm_bf16_ex(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn:
     return (out[:, :n_out], lc) if last_col else out[:, :n_out]
 
 
+def split_tf32(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [..] -> [2, ..]: plane 0 = TF32-exact part (low 13 mantissa bits cleared), plane 1 = remainder."""
+    hi = (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    return torch.stack([hi, x - hi]).contiguous()
+
+
 def gemm_f32x3(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
                splits: int = 1, last_col: bool = False):
     """fp32-accurate product of fp32 matrices on the tensor cores (3xTF32).  a / b are plain fp32 matrices
-    ([M,K] or [K,M] when a_mn; [N,K] or [K,N] when b_mn); the kernel splits them into TF32 hi / lo parts itself."""
+    ([M,K] or [K,M] when a_mn; [N,K] or [K,N] when b_mn); they are split into hi/lo planes here."""
     _need_cuda(a, b)
-    ap, bp = a.contiguous(), b.contiguous()
+    ap, bp = split_tf32(a), split_tf32(b)
     atomic = splits > 1 or last_col
     n_out = N - 1 if last_col else N
     ldo = (n_out + 3) // 4 * 4
     out = (torch.zeros if atomic else torch.empty)((M, ldo), device=a.device, dtype=torch.float32)
     lc = torch.zeros(M, device=a.device, dtype=torch.float32) if last_col else None
-    check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], int(a_mn), ptr(bp), b.shape[1], int(b_mn), M, N, K, ptr(out),
-                               out.stride(0), splits, ptr(lc), cur_stream()), "dvt_gemm_f32x3")
+    check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], a.numel(), int(a_mn), ptr(bp), b.shape[1], b.numel(), int(b_mn), M, N,
+                               K, ptr(out), out.stride(0), splits, ptr(lc), cur_stream()), "dvt_gemm_f32x3")
     return (out[:, :n_out], lc) if last_col else out[:, :n_out]

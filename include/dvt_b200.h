@@ -116,13 +116,13 @@ int dvt_vit_forward(dvt_vit_t* h, const void* x, int x_dtype, int B, int H, int 
 int dvt_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
                      void* out, int ldo, int out_dtype, int splits, float* last_col_out, void* stream);
 
-/* fp32-accurate GEMM of plain fp32 operands on the tensor cores ("3xTF32"): the kernel splits every operand tile in
- * shared memory into hi = the TF32-exact part (low 13 mantissa bits zero) and lo = x - hi and accumulates
- * A_lo.B_hi + A_hi.B_lo + A_hi.B_hi in fp32.  a_mn / b_mn as in dvt_gemm_bf16_ex.  This is what the stage-1 fit uses
- * for nn.Linear forward/backward (the reference runs them in fp32 on cuBLAS: dvt/models/neural_feature_field.py:40-44,
- * dvt/models/offline_denoiser.py:40-46 with --dtype float32). */
-int dvt_gemm_f32x3(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K, float* out,
-                   int ldo, int splits, float* last_col_out, void* stream);
+/* fp32-accurate GEMM on the tensor cores ("3xTF32"): every fp32 operand is given as two planes, hi = the TF32-exact
+ * part (low 13 mantissa bits zero) at the pointer and lo = x - hi at pointer + plane (elements); the kernel
+ * accumulates A_hi.B_hi + A_hi.B_lo + A_lo.B_hi in fp32.  a_mn / b_mn as in dvt_gemm_bf16_ex.  This is what the
+ * stage-1 fit uses for nn.Linear forward/backward (the reference runs them in fp32 on cuBLAS:
+ * dvt/models/neural_feature_field.py:40-44, dvt/models/offline_denoiser.py:40-46 with --dtype float32). */
+int dvt_gemm_f32x3(const float* A, int lda, size_t plane_a, int a_mn, const float* B, int ldb, size_t plane_b, int b_mn,
+                   int M, int N, int K, float* out, int ldo, int splits, float* last_col_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * multiresolution hash grid, 2-D inputs, 8 features per level (replaces tcnn.Encoding(HashGrid) created at

@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=10)
     ap.add_argument("--views", type=int, default=769)
     ap.add_argument("--configs", default="",
-                    help="';'-separated engine configurations 'pipeline:sweep_ctas[:graph_steps]', e.g. '1:48,32;0:0:20'")
+                    help="';'-separated engine configurations 'pipeline:sweep_ctas[:graph_steps[:pdl]]', e.g. '1:48,32;0:0:20:0'")
     ap.add_argument("--graphs-only", action="store_true")
     a = ap.parse_args()
     C, h, w, V, bsz = 768, 37, 37, a.views, 2048
@@ -39,7 +39,9 @@ def main():
             os.environ["DVT_FIT_SWEEP_CTAS"] = parts[1]
             if len(parts) > 2:
                 gsteps = int(parts[2])
-            print(f"== pipeline={parts[0]} sweep_ctas={parts[1]} graph_steps={gsteps}", flush=True)
+            if len(parts) > 3:
+                os.environ["DVT_FIT_PDL"] = parts[3]
+            print(f"== pipeline={parts[0]} sweep_ctas={parts[1]} graph_steps={gsteps} pdl={os.environ.get('DVT_FIT_PDL', 'default')}", flush=True)
         eng = FitEngine(C, h, w, bsz, field.meta)
         eng.load_modules(den, field)
         time_engine(eng, a, bank, coords, idx, (gsteps,) if a.graphs_only else (gsteps, 0))

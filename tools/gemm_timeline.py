@@ -22,13 +22,13 @@ for (M, N, K, amn, bmn, label) in [(2048, 384, 128, False, False, "G1 fwd K=128"
         ops.gemm_f32x3(a, b, M, N, K, a_mn=amn, b_mn=bmn)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ap, bp = a.contiguous(), b.contiguous()
+    ap, bp = ops.split_tf32(a), ops.split_tf32(b)
     out = torch.empty(M, N, device="cuda")
     for _ in range(200):  # keep the GPU busy so that the clocks are up when the measured launch runs
-        check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], int(amn), ptr(bp), b.shape[1], int(bmn), M, N, K,
+        check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], a.numel(), int(amn), ptr(bp), b.shape[1], b.numel(), int(bmn), M, N, K,
                                    ptr(out), N, 1, None, None))
     e0.record()
-    check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], int(amn), ptr(bp), b.shape[1], int(bmn), M, N, K,
+    check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], a.numel(), int(amn), ptr(bp), b.shape[1], b.numel(), int(bmn), M, N, K,
                                ptr(out), N, 1, None, None))
     e1.record()
     torch.cuda.synchronize()
