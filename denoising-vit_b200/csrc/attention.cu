@@ -10,10 +10,17 @@
 //              O_j = P_j.V_j (M128 N64 K16 x8; P from smem K-major, V straight from its TMA tile as an MN-major
 //              operand) into one of two TMEM buffers
 //   warps 2-5  softmax: one thread per query row (TMEM lane = row): tcgen05.ld S, online max / exp2 / sum in
-//              fp32, P -> bf16 into 128B-swizzled smem, O accumulated in registers (acc = (acc + O_{j-1}) * alpha)
+//              fp32, P -> bf16 into 128B-swizzled smem.
+//              LAZY = true (default): O accumulates in TMEM across all key tiles; the running maximum a row uses is only
+//              raised when it grows by more than 2^8 (then the row's O is rescaled in TMEM: tcgen05.ld / st, a rare,
+//              warp-uniform branch), so the S tile is read from TMEM once, lives in registers, and there is no per-tile
+//              fold of O.  exp2(s - m_stale) <= 256 is harmless in fp32 / bf16 and cancels in the final O / l.
+//              LAZY = false (DVT_ATTN_LAZY=0): O accumulated in registers (acc = (acc + O_{j-1}) * alpha), two O buffers.
 // Reference semantics: timm Attention.forward, restated at evaluation/vitdet/vision_transformer.py:73-91
 // (scale d^-0.5, no mask, softmax over keys).
 #include "common.cuh"
+
+#include <cstdlib>
 
 namespace dvt {
 
@@ -45,6 +52,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+template <bool LAZY>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int C,
                     float scale_log2e) {
@@ -96,6 +104,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // PDL: the set-up above overlapped the tail of the QKV GEMM
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -148,10 +158,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           const uint64_t da = make_smem_desc(p_base + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 0, 1024, 2);
           // V tile rows are keys (K dim), 128 B each: 16 keys per MMA = 2048 B; 8-row groups 1024 B apart
           const uint64_t db = make_smem_desc(v_base + k * 2048, 0, 1024, 2);
-          umma_f16(tmem_base + ATT_TM_O + st * 64, da, db, idesc_o, k > 0);
+          if (LAZY) umma_f16(tmem_base + ATT_TM_O, da, db, idesc_o, (j > 0) || (k > 0));  // one O, all key tiles
+          else umma_f16(tmem_base + ATT_TM_O + st * 64, da, db, idesc_o, k > 0);
         }
         umma_commit(&v_empty[st]);
-        umma_commit(&o_full[st]);
+        umma_commit(&o_full[LAZY ? 0 : st]);  // LAZY: "PV_j done" (P buffer and O free), phase j & 1
       }
     }
   } else {
@@ -159,6 +170,119 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    if constexpr (LAZY) {
+      float m_run = -INFINITY;  // the maximum (of s * scale_log2e) this row's P / O / l are currently relative to
+      float l_run = 0.f;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(s_full, j & 1, 17);
+        tc_fence_after();
+        uint32_t sreg[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(lane_addr + ATT_TM_S + c * 32, sreg[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_empty);  // S_j lives in registers now: QK of tile j+1 may overwrite the TMEM buffer
+        const int kbase = j * ATT_BK;
+        const bool partial = kbase + ATT_BK > N;  // only the last tile can hold keys >= N
+        float m_tile = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int nval = partial ? N - kbase - c * 32 : 32;  // valid keys in this chunk (warp-uniform)
+          if (nval >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sreg[c][i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nval) m_tile = fmaxf(m_tile, __uint_as_float(sreg[c][i]));
+          }
+        }
+        m_tile *= scale_log2e;                      // scale > 0: max commutes with the scaling
+        const float m_new = fmaxf(m_run, m_tile);  // finite: every tile has at least one valid key
+        const bool grow = m_new - m_run > 8.0f;     // (first tile: m_run = -inf)
+        const float m_use = grow ? m_new : m_run;
+        const float alpha = grow ? ex2(m_run - m_new) : 1.0f;  // 0 on the first tile
+        uint32_t packed[4][16];
+        float l_tile = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int nval = partial ? N - kbase - c * 32 : 32;
+          if (nval >= 32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
+              const float p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
+              l_tile += p0 + p1;
+              packed[c][i] = pack_bf16x2(p0, p1);
+            }
+          } else {  // tail of the last key tile: keys >= N contribute neither to P nor to the row sum
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p0 = 0.f, p1 = 0.f;
+              if (2 * i < nval) p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
+              if (2 * i + 1 < nval) p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
+              l_tile += p0 + p1;
+              packed[c][i] = pack_bf16x2(p0, p1);
+            }
+          }
+        }
+        if (j > 0) {
+          // PV_{j-1} must have completed before the P buffer is overwritten / O is rescaled
+          mbar_wait(&o_full[0], (j - 1) & 1, 18);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {  // rare after the first tiles; tcgen05.ld / st are warp-collective
+            uint32_t o[2][32];
+            tmem_ld_32x32(lane_addr + ATT_TM_O, o[0]);
+            tmem_ld_32x32(lane_addr + ATT_TM_O + 32, o[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < ATT_D; ++d) o[d >> 5][d & 31] = __float_as_uint(__uint_as_float(o[d >> 5][d & 31]) * alpha);
+            tmem_st_32x32(lane_addr + ATT_TM_O, o[0]);
+            tmem_st_32x32(lane_addr + ATT_TM_O + 32, o[1]);
+            tmem_st_wait();
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // keys [c*32, c*32+32) -> k-atom (c >> 1), 16B chunks ((c & 1) * 4 + q), q = 0..3
+          uint8_t* atom = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
+            *reinterpret_cast<uint4*>(atom + chunk * 16) =
+                make_uint4(packed[c][4 * q], packed[c][4 * q + 1], packed[c][4 * q + 2], packed[c][4 * q + 3]);
+          }
+        }
+        fence_async_smem();  // generic-proxy writes of P -> visible to tcgen05.mma
+        tc_fence_before();
+        mbar_arrive(p_full);
+        l_run = l_run * alpha + l_tile;
+        m_run = m_use;
+      }
+      // O of all tiles
+      mbar_wait(&o_full[0], (T - 1) & 1, 19);
+      tc_fence_after();
+      uint32_t o[2][32];
+      tmem_ld_32x32(lane_addr + ATT_TM_O, o[0]);
+      tmem_ld_32x32(lane_addr + ATT_TM_O + 32, o[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      const float inv = 1.0f / l_run;
+      const int q = q0 + row;
+      if (q < N) {
+        __nv_bfloat16* dst = out + ((size_t)b * N + q) * C + head * ATT_D;
+#pragma unroll
+        for (int d8 = 0; d8 < 8; ++d8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int d = d8 * 8 + 2 * i;
+            w[i] = pack_bf16x2(__uint_as_float(o[d >> 5][d & 31]) * inv, __uint_as_float(o[(d + 1) >> 5][(d + 1) & 31]) * inv);
+          }
+          *reinterpret_cast<uint4*>(dst + d8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    } else {
     float acc[ATT_D];
 #pragma unroll
     for (int d = 0; d < ATT_D; ++d) acc[d] = 0.f;
@@ -281,6 +405,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         }
       }
     }
+    }  // !LAZY
   }
 
   tc_fence_before();
@@ -350,8 +475,12 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     return DVT_OK;
   }
   static bool attr_set = false;  // (attention is never launched inside a stream capture)
+  static bool lazy = true;
   if (!attr_set) {
-    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    const char* v = getenv("DVT_ATTN_LAZY");
+    lazy = !(v && v[0] == '0');
     attr_set = true;
   }
   CUtensorMap tm;
@@ -359,7 +488,9 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
                         (uint64_t)N * 3 * C * 2, ATT_D, ATT_BK);
   if (rc) return rc;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
-  attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(tm, out, N, C, scale * 1.4426950408889634f);
+  const float sl2 = scale * 1.4426950408889634f;
+  if (lazy) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<true>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
+  else DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<false>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;

@@ -345,6 +345,9 @@ int num_sms();
 
 // host-side tally of kernels launched by this library (graph replays add the node count of the graph)
 void count_launch(long long n = 1);
+// Set by vit_forward around its block loop: LayerNorm / attention launches then use programmatic dependent launch (each
+// process drives one GPU from one thread).
+extern bool g_vit_pdl;
 long long launch_count();
 
 }  // namespace dvt

@@ -630,6 +630,7 @@ struct Fit {
   cudaEvent_t ev_sweep[3] = {};                // completion of the sweep launched at epoch step i (slot i % 3)
   int epoch_steps = 0;                         // pipelined steps enqueued since the sweeps were last joined
   bool enc_ready = false;                      // f->enc already holds the encoding of the next step
+  int res_x3 = 1;                              // GEMM mode of the residual MLP: 1 = 3xTF32, 2 = plain TF32 (experiment)
   bool pdl = true;                             // programmatic dependent launch along the kernel chains of a step
   bool pipe[2] = {true, true};                 // software-pipelined table sweep in phase 1 / 2 (see fit_enqueue_step)
   int sweep_ctas[2] = {0, 0};                  // persistent sweep CTAs in phase 1 / 2 (0 = many small CTAs)
@@ -713,6 +714,9 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
       if (got >= 1) { cfg[0] = a; cfg[1] = got >= 2 ? b : a; }
     }
     //   DVT_FIT_PDL=0               plain stream-ordered launches (no programmatic dependent launch)
+    //   DVT_FIT_RES_TF32=1          residual-MLP GEMMs in plain TF32 instead of 3xTF32 (experiment; not the default)
+    const char* rt = getenv("DVT_FIT_RES_TF32");
+    f->res_x3 = (rt && rt[0] == '1') ? 2 : 1;
     const char* pd = getenv("DVT_FIT_PDL");
     f->pdl = !(pd && pd[0] == '0');
     const char* pe = getenv("DVT_FIT_PIPELINE");
@@ -953,29 +957,29 @@ struct Op {
 
 // Y = act(X W^T + b):  X [M, K] planes, W [N, K] planes.  split_out: Y is written as hi/lo planes (feeds a GEMM).
 static int fit_linear(Op X, int M, int K, Op W, int N, const float* bias, int act, float* out, int ldo, size_t out_plane,
-                      bool split_out, cudaStream_t st, int impl, bool pdl = false) {
+                      bool split_out, cudaStream_t st, int impl, bool pdl = false, int x3 = 1) {
   GemmEpi e;
   e.bias = bias; e.act = act; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
   e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
   GemmShape s{M, N, K, 1};
-  s.x3 = 1; s.plane_a = X.plane; s.plane_b = W.plane; s.pdl = pdl;
+  s.x3 = x3; s.plane_a = X.plane; s.plane_b = W.plane; s.pdl = pdl;
   return launch_gemm_tn(X.p, X.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
 // dX = (dY . W) * (H > 0):  dY [M, Nout] K-major A; W stored [Nout, Kin] = MN-major B with N = Kin
 static int fit_dgrad(Op dY, int M, int Nout, Op W, int Kin, const float* Hmask, int ldmask, float* out, int ldo,
-                     size_t out_plane, bool split_out, cudaStream_t st, int impl, bool pdl = false) {
+                     size_t out_plane, bool split_out, cudaStream_t st, int impl, bool pdl = false, int x3 = 1) {
   GemmEpi e;
   e.mask_f32 = Hmask; e.ldmask = ldmask; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
   e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
   GemmShape s{M, Kin, Nout, 1};
-  s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = W.plane; s.pdl = pdl;
+  s.b_mn = 1; s.x3 = x3; s.plane_a = dY.plane; s.plane_b = W.plane; s.pdl = pdl;
   return launch_gemm_tn(dY.p, dY.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
 // dW[Nout, Kin] (+ db[Nout]) += dY^T . [X | 1]:  dY stored [n, Nout] (MN-major A), X stored [n, Kin + ones] (MN-major B)
 static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb, cudaStream_t st, int impl,
-                     bool pdl = false) {
+                     bool pdl = false, int x3 = 1) {
   GemmEpi e;
   e.out = gW; e.ldo = Kin; e.out_mode = OUT_F32_ATOMIC; e.last_col_out = gb;
   // split-K so that (output tiles x splits) fills the SMs once: tiles are 128 x 64, k-blocks 32 samples
@@ -983,7 +987,7 @@ static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb
   const int tiles = ((Nout + 127) / 128) * ((Kin + 1 + 63) / 64);
   int splits = std::max(1, std::min(num_sms() / std::max(tiles, 1), kb / 4));
   GemmShape s{Nout, Kin + 1, n, splits};
-  s.a_mn = 1; s.b_mn = 1; s.x3 = 1; s.plane_a = dY.plane; s.plane_b = X.plane; s.pdl = pdl;
+  s.a_mn = 1; s.b_mn = 1; s.x3 = x3; s.plane_a = dY.plane; s.plane_b = X.plane; s.pdl = pdl;
   return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
 }
 
@@ -1063,9 +1067,9 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   const bool pipe = f->pipe[phase2 ? 1 : 0];
   if (!pipe) FIT_RC(fit_enqueue_encode(f, step_off, 0, st));  // else f->enc is already this step's (fit_run)
   if (phase2) {
-    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl, pdl));
-    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl, pdl));
-    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl, pdl));
+    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl, pdl, f->res_x3));
+    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl, pdl, f->res_x3));
+    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl, pdl, f->res_x3));
   }
   FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl, pdl));
   FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl, pdl));
@@ -1098,13 +1102,13 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   if (phase2) {
     // residual MLP backward: the data-gradient chain on side C, the weight-gradient GEMMs that do not feed it on side E
     //   side C: dr2 = dR.R3 -> dr1 = dr2.R2 -> dR1      side E: dR3 (needs dR, r2 only) -> [dr2 ready] dR2
-    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, sC, impl, pdl));
+    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, sC, impl, pdl, f->res_x3));
     DVT_CUDA_OK(cudaEventRecord(f->ev[12], sC));                                              // dr2 ready
-    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, sC, impl, pdl));
-    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl, pdl));
-    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sE, impl, pdl));
+    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, sC, impl, pdl, f->res_x3));
+    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl, pdl, f->res_x3));
+    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sE, impl, pdl, f->res_x3));
     DVT_CUDA_OK(cudaStreamWaitEvent(sE, f->ev[12], 0));
-    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sE, impl, pdl));
+    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sE, impl, pdl, f->res_x3));
     FIT_RC(join(sC, f->ev[5]));
     FIT_RC(join(sE, f->ev[13]));
   }

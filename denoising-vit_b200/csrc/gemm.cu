@@ -12,6 +12,7 @@
 // (reference: dvt/models/neural_feature_field.py:40-44, dvt/models/offline_denoiser.py:40-46).
 #include "gemm.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace dvt {
@@ -224,9 +225,14 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               constexpr uint32_t lt_a = A_MN ? 1 : 2, lt_b = B_MN ? 1 : 2;
               const uint64_t dah = make_smem_desc(a_base + ka, lbo_a, sbo_a, lt_a), dal = make_smem_desc(a_lo + ka, lbo_a, sbo_a, lt_a);
               const uint64_t dbh = make_smem_desc(b_base + kbb, lbo_b, sbo_b, lt_b), dbl = make_smem_desc(b_lo + kbb, lbo_b, sbo_b, lt_b);
-              umma_tf32(d_tmem, dal, dbh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);  // small terms first
-              umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-              umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+              const uint32_t acc0 = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (s.x3 == 1) {
+                umma_tf32(d_tmem, dal, dbh, idesc, acc0);  // small terms first
+                umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+              } else {  // x3 == 2: plain TF32 product of the hi parts (same operand layout, a third of the MMA work)
+                umma_tf32(d_tmem, dah, dbh, idesc, acc0);
+              }
             }
           } else {
             const uint64_t da = make_smem_desc(a_base, A_MN ? BK * 128 : 0, 1024, 2);
@@ -455,7 +461,16 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s
   using L = GemmSmem<BN, STAGES, X3>;
   auto kern = gemm_tn_tc_kernel<BN, STAGES, TF32, A_MN, B_MN, X3>;
   const int tiles = ((s.M + BM - 1) / BM) * ((s.N + BN - 1) / BN) * s.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  // DVT_GEMM_TILES_PER_CTA=n (n > 0) bounds the tiles one CTA works through, i.e. launches more, shorter-lived CTAs than
+  // SMs: a persistent CTA keeps its SM for the whole kernel, which starves concurrent high-priority streams (the fit
+  // running beside the next image's ViT forwards); short-lived CTAs hand SMs over every few microseconds instead.
+  static int tiles_per_cta = -1;
+  if (tiles_per_cta < 0) {
+    const char* v = getenv("DVT_GEMM_TILES_PER_CTA");
+    tiles_per_cta = v ? atoi(v) : 0;
+  }
+  if (!X3 && tiles_per_cta > 0) grid = std::max(grid, (tiles + tiles_per_cta - 1) / tiles_per_cta);
   DVT_CUDA_OK(launch_k(s.pdl != 0, kern, dim3(grid), dim3(L::THREADS), (size_t)L::TOTAL, stream, tmA, tmB, s, e));
   count_launch();
   DVT_CUDA_OK(cudaGetLastError());

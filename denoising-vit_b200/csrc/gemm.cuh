@@ -50,7 +50,7 @@ struct GemmShape {
   // 3xTF32 ("x3"): fp32-accurate product on the tensor cores.  Each fp32 operand is stored as two planes
   // (hi = TF32-exact part at the base pointer, lo = remainder at base + plane elements) and the kernel accumulates
   // A_hi.B_hi + A_hi.B_lo + A_lo.B_hi.
-  int x3 = 0;
+  int x3 = 0;    // 1: 3xTF32 as described; 2: same operand layout, but only A_hi.B_hi (plain TF32 accuracy)
   size_t plane_a = 0, plane_b = 0;
   int pdl = 0;   // launch with programmatic stream serialisation (the kernel calls pdl_wait() after its set-up)
 };

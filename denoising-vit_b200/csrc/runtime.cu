@@ -10,6 +10,8 @@
 
 namespace dvt {
 
+bool g_vit_pdl = false;
+
 namespace {
 thread_local char g_err[1024] = "";
 }

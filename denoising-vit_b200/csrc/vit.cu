@@ -11,6 +11,8 @@
 // Blocks after `layer_index` are skipped: the reference runs them (no stop_early) but they cannot change the
 // requested output.
 #include "common.cuh"
+
+#include <cstdlib>
 #include "gemm.cuh"
 
 #include <string>
@@ -210,6 +212,19 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
   count_launch();
 
   const int Mi = (int)M;
+  // Programmatic dependent launch along the block stack is available (DVT_VIT_PDL=1) but OFF by default: these kernels
+  // run for 25-200 us each, so the hidden launch latency is worth < 1 %, and CTAs that are resident early but blocked in
+  // griddepcontrol.wait take SM slots from the fit running beside the forwards (measured: 803.7 vs 784.5 ms / image,
+  // profiles/r1x_validate.txt).  The fit's 10-20 us kernels are where PDL pays (fit.cu).
+  static int vit_pdl = -1;
+  if (vit_pdl < 0) {
+    const char* pv = getenv("DVT_VIT_PDL");
+    vit_pdl = (pv && pv[0] == '1') ? 1 : 0;
+  }
+  struct PdlScope {
+    PdlScope(bool on) { g_vit_pdl = on; }
+    ~PdlScope() { g_vit_pdl = false; }
+  } pdl_scope(vit_pdl != 0);
   for (int i = 0; i <= layer_index; ++i) {
     const VitBlock& b = v->blocks[i];
     rc = launch_layernorm(v->x, C, b.n1w, b.n1b, v->xn, C, true, Mi, C, v->ln_eps, 1, 0, stream);
@@ -217,6 +232,7 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
     {
       GemmEpi e; e.bias = b.qkv_b; e.out_mode = OUT_BF16; e.out = v->qkv; e.ldo = 3 * C;
       GemmShape s{Mi, 3 * C, C, 1};
+      s.pdl = vit_pdl;
       rc = launch_gemm_tn(v->xn, C, b.qkv_w, C, TMAP_BF16, s, e, stream, gi);
       if (rc) return rc;
     }
@@ -226,6 +242,7 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
       GemmEpi e; e.bias = b.proj_b; e.out_mode = OUT_F32_RESID; e.out = v->x; e.ldo = C;
       e.gamma = v->layerscale ? b.ls1 : nullptr;
       GemmShape s{Mi, C, C, 1};
+      s.pdl = vit_pdl;
       rc = launch_gemm_tn(v->attn, C, b.proj_w, C, TMAP_BF16, s, e, stream, gi);
       if (rc) return rc;
     }
@@ -237,6 +254,7 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
       GemmEpi e; e.bias = b.fc1_b; e.act = v->swiglu ? ACT_NONE : ACT_GELU; e.out_mode = OUT_BF16; e.out = v->hid;
       e.ldo = v->mlp_hidden;
       GemmShape s{Mi, v->mlp_hidden, C, 1};
+      s.pdl = vit_pdl;
       rc = launch_gemm_tn(v->xn, C, b.fc1_w, C, TMAP_BF16, s, e, stream, gi);
       if (rc) return rc;
     }
@@ -251,6 +269,7 @@ int vit_forward(Vit* v, const void* x_in, bool x_bf16, int B, int H, int W, int 
       GemmEpi e; e.bias = b.fc2_b; e.out_mode = OUT_F32_RESID; e.out = v->x; e.ldo = C;
       e.gamma = v->layerscale ? b.ls2 : nullptr;
       GemmShape s{Mi, C, fc2_k, 1};
+      s.pdl = vit_pdl;
       rc = launch_gemm_tn(fc2_in, fc2_k, b.fc2_w, fc2_k, TMAP_BF16, s, e, stream, gi);
       if (rc) return rc;
     }

@@ -17,13 +17,16 @@ template <typename OutT, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                  OutT* __restrict__ y, int ldy, int rows, int C, float eps, int in_group, int skip) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // grid-stride over rows: the grid is one full wave of CTAs, so there is no partially filled last wave
+  for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < rows; warp += nwarps) {
   int out_row = warp;
   if (skip > 0) {
     const int g = warp / in_group, t = warp - g * in_group;
-    if (t < skip) return;
+    if (t < skip) continue;
     out_row = g * (in_group - skip) + (t - skip);
   }
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * ldx);
@@ -70,12 +73,29 @@ layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
       }
     }
   }
+  }  // rows
+}
+
+// one full wave of CTAs (occupancy x #SM), rows are taken grid-stride
+template <typename OutT, int NV>
+static void launch_ln_one(int want_blocks, int threads, cudaStream_t stream, const float* x, int ldx, const float* gamma,
+                          const float* beta, OutT* y, int ldy, int rows, int C, float eps, int in_group, int skip) {
+  static int wave = 0;
+  if (wave == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_kernel<OutT, NV>, threads, 0) != cudaSuccess || occ < 1)
+      occ = 1;
+    wave = occ * num_sms();
+  }
+  const int blocks = want_blocks < wave ? want_blocks : wave;
+  launch_k(g_vit_pdl, layernorm_kernel<OutT, NV>, dim3(blocks), dim3(threads), 0, stream, x, ldx, gamma, beta, y, ldy, rows, C,
+           eps, in_group, skip);
 }
 
 template <typename OutT>
 static void launch_ln_nv(int nv, int blocks, int threads, cudaStream_t stream, const float* x, int ldx, const float* gamma,
                          const float* beta, OutT* y, int ldy, int rows, int C, float eps, int in_group, int skip) {
-#define DVT_LN(NV) layernorm_kernel<OutT, NV><<<blocks, threads, 0, stream>>>(x, ldx, gamma, beta, y, ldy, rows, C, eps, in_group, skip)
+#define DVT_LN(NV) launch_ln_one<OutT, NV>(blocks, threads, stream, x, ldx, gamma, beta, y, ldy, rows, C, eps, in_group, skip)
   if (nv <= 3) DVT_LN(3);
   else if (nv <= 6) DVT_LN(6);
   else if (nv <= 8) DVT_LN(8);
@@ -90,7 +110,7 @@ int launch_layernorm(const float* x, int ldx, const float* gamma, const float* b
               ldx, ldy);
   if (rows <= 0) return DVT_OK;
   const int threads = 256;
-  const int blocks = (rows * 32 + threads - 1) / threads;
+  const int blocks = (rows * 32 + threads - 1) / threads;  // upper bound; launch_ln_one caps it at one full wave
   const int nv = (C / 4 + 31) / 32;
   const int grp = in_group > 0 ? in_group : 1;
   if (out_bf16)

@@ -30,7 +30,7 @@ def main():
         d = dict(zip(hdr, r))
         lines.append(f"## launch: {d.get('Kernel Name', '?')[:150]}")
         for k in hdr:
-            if k in WANT:
+            if k in WANT or ("inst_executed_pipe_" in k and "pct_of_peak_sustained_active" in k and k.startswith("sm__")):
                 lines.append(f"{k:90s} {d[k]}")
         lines.append("")
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
@@ -50,12 +50,13 @@ def main():
                     tot[s] += int(r[ix[s]])
                 except Exception:
                     pass
-            top.append((n, r[ix["Source"]][:110]))
+            why = sorted(((int(r[ix[s_]] or 0), s_[6:]) for s_ in stalls if (r[ix[s_]] or "0").isdigit()), reverse=True)[:2]
+            top.append((n, r[ix["Source"]][:90] + "   <- " + ", ".join(f"{w}:{c}" for c, w in why if c)))
         lines.append(f"## warp-stall sampling (first launch), {total} samples")
         for s, v in sorted(tot.items(), key=lambda x: -x[1])[:8]:
             lines.append(f"{s:28s}{v:8d} {100.0 * v / max(total, 1):5.1f}%")
         lines.append("## hottest SASS lines")
-        for n, s in sorted(top, reverse=True)[:15]:
+        for n, s in sorted(top, reverse=True)[:40]:
             lines.append(f"{n:7d}  {s}")
     open(out, "w").write("\n".join(lines) + "\n")
     print("wrote", out)
