@@ -46,16 +46,96 @@ def parse():
     ap.add_argument("--graph-steps", type=int, default=20)
     ap.add_argument("--no-overlap", action="store_true", help="one image strictly after the other (A/B of the schedule)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", action="store_true",
+                    help="skip the stand-alone kernel timings (for ncu launch lists of the timed region)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
 def peaks():
+    """HBM copy bandwidth and dense bf16 throughput: the driver-written MEASURED_PEAKS.json (burst figure for a kernel
+    timed alone, sustained one for a path timed inside a long step), else the fallback of B200_PROFILING.md."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         d = json.load(open(path))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "bf16_tflops_burst": d["bf16_tflops"], "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(path):
+        return json.load(open(path)).get(kernel, {}).get("dram_bytes_per_launch")
+    return None
+
+
+def kernel_rooflines(pipe, extract_bsz, dev):
+    """The two kernels that dominate the step, each timed ALONE with CUDA events on the stream it is launched on
+    (10 launches after 3 warm-ups, L2 flushed by a 256 MB write before every launch), through the library's unit entry
+    points -- the same kernels, shapes and epilogues the timed region launches:
+      * gemm_tn_tc_kernel<256, 3> (bf16 tcgen05 GEMM): the four GEMMs of one ViT-B block at the extraction batch
+        (QKV, out-proj + LayerScale residual, fc1 + GELU, fc2 + LayerScale residual); algorithmic flops =
+        SURVEY.md 8(d) per-view figures (4.85 + 1.62 + 12.93 GF) x views per launch set;
+      * fit_adam_table_kernel (dense Adam sweep of the hash table): algorithmic bytes = 24 B x 19 741 760 parameters."""
+    from dvt import ops
+    g = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *sh: torch.randn(*sh, device=dev, generator=g)  # noqa: E731
+    Bv, N, C = extract_bsz, 1370, 768
+    M = Bv * N
+    x, xn, hid = rn(M, C), rn(M, C).bfloat16(), rn(M, 4 * C).bfloat16()
+    w_qkv, b_qkv = (rn(3 * C, C) / 28).bfloat16(), rn(3 * C)
+    w_proj, b_proj = (rn(C, C) / 28).bfloat16(), rn(C)
+    w_fc1, b_fc1 = (rn(4 * C, C) / 28).bfloat16(), rn(4 * C)
+    w_fc2, b_fc2 = (rn(C, 4 * C) / 55).bfloat16(), rn(C)
+    gam = torch.full((C,), 1e-3, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    gemms = [lambda: ops.gemm_tn(xn, w_qkv, b_qkv, None, torch.bfloat16),
+             lambda: ops.gemm_tn_residual_(x, xn, w_proj, b_proj, gam),
+             lambda: ops.gemm_tn(xn, w_fc1, b_fc1, "gelu", torch.bfloat16),
+             lambda: ops.gemm_tn_residual_(x, hid, w_fc2, b_fc2, gam)]
+
+    def time_alone(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts))
+
+    gemm_ms = [time_alone(fn) for fn in gemms]
+    gemm_flops = Bv * (4.85e9 + 1.62e9 + 12.93e9)
+    del flush
+
+    def time_stream(fn, reps=20, warm=3):
+        """Back-to-back launches between two events: the sweep streams 474 MB per launch, far more than the L2 holds."""
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    sweep_ctas = int(os.environ.get("DVT_FIT_SWEEP_CTAS", "40").split(",")[0])  # geometry of the timed region (fit.cu default)
+    sweep_ms = time_stream(lambda: pipe.engine.sweep_once(max(sweep_ctas, 0)))
+    sweep_full_ms = time_stream(lambda: pipe.engine.sweep_once(0))
+    sweep_bytes = 24.0 * pipe.field.neural_field.params.numel()
+    gbs = lambda ms: sweep_bytes / (ms / 1e3) / 1e9  # noqa: E731
+    return {"gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / (sum(gemm_ms) / 1e3) / 1e12, "gemm_flops": gemm_flops,
+            "sweep_ms": sweep_ms, "sweep_gbs": gbs(sweep_ms), "sweep_bytes": sweep_bytes, "sweep_ctas": sweep_ctas,
+            "sweep_full_ms": sweep_full_ms, "sweep_full_gbs": gbs(sweep_full_ms)}
 
 
 class ClockSampler:
@@ -145,6 +225,7 @@ def cpu_reference_rate(args, views_sample: int = 1, fit_steps: int = 2):
         dt = time.perf_counter() - t0
         if step not in (0, T // 2 + 1):  # first step of each phase = warm-up
             times[phase2].append(dt)
+    assert times[False] and times[True], "cpu_reference_rate: fit_steps must be >= 2 (one timed step per phase)"
     t_p1, t_p2 = float(np.mean(times[False])), float(np.mean(times[True]))
     n_p2 = args.num_iters - 1 - int(0.5 * args.num_iters)
     n_p1 = args.num_iters - n_p2
@@ -162,7 +243,7 @@ def run_reference_arm(args, rank):
     vals, last = [], None
     for _ in range(max(1, args.warmup > 0) + args.steps):
         t0 = time.perf_counter()
-        last = cpu_reference_rate(args, views_sample=1, fit_steps=1)
+        last = cpu_reference_rate(args, views_sample=1, fit_steps=2)
         vals.append((last["value"], time.perf_counter() - t0))
     vals = vals[1:] if len(vals) > 1 else vals
     v = float(np.mean([a for a, _ in vals]))
@@ -308,19 +389,45 @@ def main():
         e2e = {"value": world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps}
 
+    kr = kernel_rooflines(pipe, args.extract_bsz, dev) if rank == 0 and not args.no_kernel_rooflines else None
+    if kr is None and rank == 0:
+        kr = {"gemm_ms": None, "gemm_tflops": float("nan"), "gemm_flops": None, "sweep_ms": None, "sweep_gbs": float("nan"),
+              "sweep_bytes": None, "sweep_ctas": None, "sweep_full_ms": None, "sweep_full_gbs": float("nan")}
+
     if rank == 0:
         pk = peaks()
         n_p2 = args.num_iters - 1 - int(0.5 * args.num_iters)
         n_p1 = args.num_iters - n_p2
+        # kernel level (the contract).  Largest shares of the ncu launch list of this command
+        # (profiles/*_launch_shares.txt): the dense Adam sweep, then the bf16 GEMM.
+        gemm = {"bound": "tensor", "achieved": kr["gemm_tflops"], "peak": pk["bf16_tflops_burst"], "unit": "TFLOP/s",
+                    "frac": kr["gemm_tflops"] / pk["bf16_tflops_burst"], "traffic": ncu_traffic("gemm_tn_tc_kernel<256,3,bf16>"),
+                    "kernel": "gemm_tn_tc_kernel<256, 3> (bf16 tcgen05 GEMM, the 4 GEMMs of one ViT-B block)",
+                    "algorithmic_flops_per_launch_set": kr["gemm_flops"], "ms_per_launch": kr["gemm_ms"],
+                    "views_per_launch": args.extract_bsz, "timed": "alone, CUDA events, L2 flushed between launches",
+                    "peak_source": pk["source"] + " (bf16 cuBLAS burst: kernel timed alone)"}
+        dominant = {"bound": "hbm", "achieved": kr["sweep_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": kr["sweep_gbs"] / pk["hbm_gbs"], "traffic": ncu_traffic("fit_adam_table_kernel"),
+                    "kernel": "fit_adam_table_kernel (dense Adam sweep of the 19.74 M-parameter hash table), launched as in the "
+                              f"timed region: {kr['sweep_ctas']} persistent 1024-thread CTAs (it shares the GPU with the GEMM "
+                              "chains of the next two steps, so it is deliberately kept off the other SMs)",
+                    "algorithmic_bytes_per_launch": kr["sweep_bytes"], "ms_per_launch": kr["sweep_ms"],
+                    "full_grid": {"ms_per_launch": kr["sweep_full_ms"], "achieved": kr["sweep_full_gbs"],
+                                  "frac": kr["sweep_full_gbs"] / pk["hbm_gbs"],
+                                  "note": "same kernel on 8 x #SM CTAs of 256 threads (the sequential schedule's geometry)"},
+                    "timed": "alone, CUDA events around 20 back-to-back launches (474 MB per launch >> L2)",
+                    "peak_source": pk["source"] + " (copy bandwidth)"}
+        # path level, from the CUDA-event spans INSIDE the timed region (the two paths of neighbouring images overlap,
+        # so each span is stretched by the other path's share of the SMs / HBM)
         hp1_tf = V * FLOPS_PER_VIEW / (hp1_ms / 1e3) / 1e12
         hp2_gbs = (n_p1 * FIT_BYTES_P1 + n_p2 * FIT_BYTES_P2) / (hp2_ms / 1e3) / 1e9
         r1 = {"bound": "tensor", "achieved": hp1_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-              "frac": hp1_tf / pk["bf16_tflops"], "traffic": None, "kernel": "HP-1: 769 ViT-B/14 forwards (tcgen05 GEMMs + "
-              "flash attention)", "ms_per_image": hp1_ms, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)"}
+              "frac": hp1_tf / pk["bf16_tflops"], "traffic": None, "kernel": "path HP-1: 769 ViT-B/14 forwards (tcgen05 GEMMs "
+              "+ flash attention + LayerNorm)", "ms_per_image": hp1_ms, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)"}
         r2 = {"bound": "hbm", "achieved": hp2_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hp2_gbs / pk["hbm_gbs"],
-              "traffic": None, "kernel": "HP-2: 2000-step neural-field fit (dense Adam sweep dominates)",
+              "traffic": None, "kernel": "path HP-2: 2000-step neural-field fit (SURVEY 8(d) algorithmic bytes / span)",
               "ms_per_image": hp2_ms, "peak_source": pk["source"] + " (copy bandwidth)"}
-        dominant, other = (r1, r2) if hp1_ms >= hp2_ms else (r2, r1)
+        other = [gemm, r1, r2]
         line = {"metric": "images/sec stage-1 denoise (ViT-B/14, 518^2, 2k-iter fit)", "value": value, "unit": "images/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (ViT) / tf32x3 (fit)",

@@ -30,7 +30,7 @@ def main():
         d = dict(zip(hdr, r))
         lines.append(f"## launch: {d.get('Kernel Name', '?')[:150]}")
         for k in hdr:
-            if k in WANT or ("inst_executed_pipe_" in k and "pct_of_peak_sustained_active" in k and k.startswith("sm__")):
+            if k in WANT or ("inst_executed_pipe_" in k and k.endswith(".avg.pct_of_peak_sustained_active") and k.startswith("sm__")):
                 lines.append(f"{k:90s} {d[k]}")
         lines.append("")
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
