@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--views", type=int, default=768)
     ap.add_argument("--num-iters", type=int, default=2000)
     ap.add_argument("--warmup-iters", type=int, default=200)
-    ap.add_argument("--extract-bsz", type=int, default=16)
+    ap.add_argument("--extract-bsz", type=int, default=32)
     ap.add_argument("--graph-steps", type=int, default=20)
     ap.add_argument("--no-overlap", action="store_true", help="one image strictly after the other (A/B of the schedule)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -96,13 +96,14 @@ def kernel_rooflines(pipe, extract_bsz, dev):
              lambda: ops.gemm_tn(xn, w_fc1, b_fc1, "gelu", torch.bfloat16),
              lambda: ops.gemm_tn_residual_(x, hid, w_fc2, b_fc2, gam)]
 
-    def time_alone(fn, reps=10, warm=3):
+    def time_alone(fn, reps=10, warm=3, flush_l2=True):
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
-            flush.zero_()
+            if flush_l2:
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -113,24 +114,11 @@ def kernel_rooflines(pipe, extract_bsz, dev):
 
     gemm_ms = [time_alone(fn) for fn in gemms]
     gemm_flops = Bv * (4.85e9 + 1.62e9 + 12.93e9)
-    del flush
-
-    def time_stream(fn, reps=20, warm=3):
-        """Back-to-back launches between two events: the sweep streams 474 MB per launch, far more than the L2 holds."""
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
     sweep_ctas = int(os.environ.get("DVT_FIT_SWEEP_CTAS", "40").split(",")[0])  # geometry of the timed region (fit.cu default)
-    sweep_ms = time_stream(lambda: pipe.engine.sweep_once(max(sweep_ctas, 0)))
-    sweep_full_ms = time_stream(lambda: pipe.engine.sweep_once(0))
+    # one event pair per launch, no flush: the sweep streams 474 MB per launch, far more than the L2 holds
+    sweep_ms = time_alone(lambda: pipe.engine.sweep_once(max(sweep_ctas, 0)), flush_l2=False)
+    sweep_full_ms = time_alone(lambda: pipe.engine.sweep_once(0), flush_l2=False)
+    del flush
     sweep_bytes = 24.0 * pipe.field.neural_field.params.numel()
     gbs = lambda ms: sweep_bytes / (ms / 1e3) / 1e9  # noqa: E731
     return {"gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / (sum(gemm_ms) / 1e3) / 1e12, "gemm_flops": gemm_flops,
@@ -388,6 +376,33 @@ def main():
         d2h = 2 * h * w * C * 4
         e2e = {"value": world * args.steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps}
+        # The same public call fed with the IMAGE instead of ready-made views: per step one pinned
+        # 3.2 MB image goes to the GPU, the 768 random-resized-crop views + their coordinate grids are generated there
+        # by dvt_view_crops (crop boxes / flips drawn on the host with the reference's RNG calls), inside the timed region.
+        from dvt.dataset import GpuViewGenerator
+        del views_host
+        gen = GpuViewGenerator((518, 518), num_views=args.views, dtype=torch.float32)
+        image_host = torch.randn(3, 518, 518, generator=torch.Generator().manual_seed(rank)).pin_memory()
+        views_buf = torch.empty((V, 3, 518, 518), device=dev, dtype=torch.float32)
+        coords_of = {}
+
+        def gen_views(i):
+            v, c = gen(image_host.to(dev, non_blocking=True), views_out=views_buf)
+            coords_of[i] = c
+            return v
+
+        def run_from_image(first, n):
+            fin = lambda i, out: (out["denoised_feats"].cpu(), out["raw"].cpu())  # noqa: E731
+            return pipe.run_images(n, gen_views, lambda i: coords_of[i], lambda i: idx_stream(first + i), fin,
+                                   overlap=not args.no_overlap)
+
+        run_from_image(0, 1)
+        ms_img, _, _ = timed(run_from_image, args.steps, collate=True)
+        e2e["from_image"] = {"value": world * args.steps / (ms_img / 1000.0), "unit": "images/s",
+                             "h2d_bytes_per_step": 3 * 518 * 518 * 4 + V * 5 * 4 + args.num_iters * 2048 * 4,
+                             "d2h_bytes_per_step": d2h, "ms_per_step": ms_img / args.steps,
+                             "note": "views generated on the GPU from one host image per step (dvt_view_crops)"}
+        del views_buf
 
     kr = kernel_rooflines(pipe, args.extract_bsz, dev) if rank == 0 and not args.no_kernel_rooflines else None
     if kr is None and rank == 0:
@@ -415,7 +430,7 @@ def main():
                     "full_grid": {"ms_per_launch": kr["sweep_full_ms"], "achieved": kr["sweep_full_gbs"],
                                   "frac": kr["sweep_full_gbs"] / pk["hbm_gbs"],
                                   "note": "same kernel on 8 x #SM CTAs of 256 threads (the sequential schedule's geometry)"},
-                    "timed": "alone, CUDA events around 20 back-to-back launches (474 MB per launch >> L2)",
+                    "timed": "alone, one CUDA-event pair per launch, 10 launches (474 MB per launch >> L2)",
                     "peak_source": pk["source"] + " (copy bandwidth)"}
         # path level, from the CUDA-event spans INSIDE the timed region (the two paths of neighbouring images overlap,
         # so each span is stretched by the other path's share of the SMs / HBM)

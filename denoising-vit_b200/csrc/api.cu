@@ -29,6 +29,8 @@ int fit_losses(Fit* f, float* dst_host, int num_iters);
 int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, int impl);
 int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, int impl);
 int fit_sweep_once(Fit* f, int ctas, cudaStream_t st);
+int view_crops(const float* image, int H, int W, const int* boxes_host, const int* flips_host, int V, void* out, bool out_bf16,
+               int OH, int OW, float* coords_out, int hp, int wp, cudaStream_t st);
 int hashgrid_corners(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
                      const uint32_t* hashed, const float* coords, int n, uint32_t* idx, float* w, cudaStream_t st);
 int hashgrid_fwd(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
@@ -266,6 +268,11 @@ int dvt_fit_residual(dvt_fit_t* h, const float* raw, int n, float* out, void* st
 int dvt_fit_sweep_once(dvt_fit_t* h, int ctas, void* stream) {
   DVT_REQUIRE(h, "dvt_fit_sweep_once: null handle");
   return fit_sweep_once(reinterpret_cast<Fit*>(h), ctas, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_view_crops(const float* image, int H, int W, const int* boxes_host, const int* flips_host, int V, void* out,
+                   int out_dtype, int OH, int OW, float* coords_out, int hp, int wp, void* stream) {
+  return view_crops(image, H, W, boxes_host, flips_host, V, out, out_dtype == DVT_DTYPE_BF16, OH, OW, coords_out, hp, wp,
+                    reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

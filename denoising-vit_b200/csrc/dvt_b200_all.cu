@@ -5,4 +5,5 @@
 #include "attention.cu"
 #include "vit.cu"
 #include "fit.cu"
+#include "views.cu"
 #include "api.cu"

@@ -53,6 +53,8 @@ SIGNATURES = {
     "dvt_fit_query": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dvt_fit_residual": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dvt_fit_sweep_once": (c_int, [c_void_p, c_int, c_void_p]),
+    "dvt_view_crops": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                               c_int, c_int, c_void_p]),
     "dvt_vit_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float]),
     "dvt_vit_destroy": (None, [c_void_p]),
     "dvt_vit_load": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),

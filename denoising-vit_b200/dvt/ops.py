@@ -1,10 +1,12 @@
 """Unit operators over torch CUDA tensors (thin wrappers around the C ABI; used by tests and by dvt.models)."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
-from ._lib import DT_BF16, DT_F32, check, cur_stream, lib, ptr
+from ._lib import DT_BF16, DT_F32, DvtError, check, cur_stream, lib, ptr  # noqa: F401
 
 _ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2}
 
@@ -120,3 +122,28 @@ def gemm_f32x3(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: b
     check(lib().dvt_gemm_f32x3(ptr(ap), a.shape[1], a.numel(), int(a_mn), ptr(bp), b.shape[1], b.numel(), int(b_mn), M, N,
                                K, ptr(out), out.stride(0), splits, ptr(lc), cur_stream()), "dvt_gemm_f32x3")
     return (out[:, :n_out], lc) if last_col else out[:, :n_out]
+
+
+def view_crops(image: torch.Tensor, boxes, flips, size, hp: int, wp: int, out: torch.Tensor | None = None,
+               coords_out: torch.Tensor | None = None, dtype: torch.dtype = torch.float32):
+    """All views of one image in one launch: out[v] = hflip?(resized_crop(image, boxes[v], size, BICUBIC, antialias=True)),
+    coords_out[v] = the (x, y) patch-coordinate grid of the crop (reference: dvt/dataset/transform.py:39-76).
+    image f32 cuda [3, H, W]; boxes int [V, 4] (top, left, height, width) and flips int [V] on the HOST."""
+    import numpy as np
+    _need_cuda(image)
+    assert image.dtype == torch.float32 and image.is_contiguous() and image.dim() == 3 and image.shape[0] == 3
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.int32).reshape(-1, 4))
+    f = np.ascontiguousarray(np.asarray(flips, dtype=np.int32).reshape(-1))
+    V = b.shape[0]
+    assert f.shape[0] == V
+    OH, OW = int(size[0]), int(size[1])
+    if out is None:
+        out = torch.empty((V, 3, OH, OW), device=image.device, dtype=dtype)
+    if coords_out is None:
+        coords_out = torch.empty((V, hp, wp, 2), device=image.device, dtype=torch.float32)
+    assert out.is_contiguous() and tuple(out.shape) == (V, 3, OH, OW) and out.dtype in (torch.float32, torch.bfloat16)
+    assert coords_out.is_contiguous() and tuple(coords_out.shape) == (V, hp, wp, 2) and coords_out.dtype == torch.float32
+    check(lib().dvt_view_crops(ptr(image), image.shape[1], image.shape[2], b.ctypes.data_as(ctypes.c_void_p),
+                               f.ctypes.data_as(ctypes.c_void_p), V, ptr(out), _dt(out), OH, OW, ptr(coords_out), hp, wp,
+                               cur_stream()), "dvt_view_crops")
+    return out, coords_out

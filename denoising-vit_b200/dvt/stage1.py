@@ -144,14 +144,19 @@ class Stage1Pipeline:
         sx = self._extract_stream if overlap else main
         tev = (lambda: torch.cuda.Event(enable_timing=True)) if events is not None else None
 
-        def enqueue_extract(i):
+        def make_views(i):
+            # views_fn may launch GPU work (GpuViewGenerator): it goes to the extraction stream, in front of the forwards
+            with torch.cuda.stream(sx):
+                return views_fn(i)
+
+        def enqueue_extract(i, views):
             slot = i % 2
             sx.wait_event(self._fit_done[slot])    # the fit that read this bank buffer two images ago
             with torch.cuda.stream(sx):
                 if tev:
                     a = tev()
                     a.record(sx)
-                bank = self.extract_bank(views_fn(i), slot=slot)
+                bank = self.extract_bank(views, slot=slot)
                 if tev:
                     b = tev()
                     b.record(sx)
@@ -163,9 +168,13 @@ class Stage1Pipeline:
             e.record(main)
         sx.wait_stream(main)                       # inputs produced on the caller's stream
         results = []
-        bank = enqueue_extract(0)
+        bank = enqueue_extract(0, make_views(0))
         idx = idx_fn(0)
         for i in range(n_images):
+            # The views of the NEXT image are produced now, i.e. behind the forwards of image i and BEFORE the fit of image i
+            # is enqueued: the fit's set-up synchronises with the device, so a view-generation kernel never runs beside the
+            # fit (a low-priority kernel of 228 k tiny CTAs beside the latency-bound fit was measured to cost 250 ms).
+            views_next = make_views(i + 1) if i + 1 < n_images else None
             main.wait_event(self._ext_done[i % 2])
             if tev:
                 a = tev()
@@ -177,7 +186,7 @@ class Stage1Pipeline:
                 events.append(("hp2", a, b))
             self._fit_done[i % 2].record(main)
             if i + 1 < n_images:                   # enqueued while the GPU runs the fit of image i
-                bank = enqueue_extract(i + 1)
+                bank = enqueue_extract(i + 1, views_next)
                 idx = idx_fn(i + 1)
             results.append(finalize(i, out))
         main.wait_stream(sx)

@@ -179,6 +179,17 @@ int dvt_fit_residual(dvt_fit_t* h, const float* raw, int n, float* out, void* st
  * state -- call after the results of the fit have been read.  Requires dvt_fit_begin. */
 int dvt_fit_sweep_once(dvt_fit_t* h, int ctas, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * view generation (the step in front of HP-1)
+ * Replaces RandomResizedCropFlip.forward (dvt/dataset/transform.py:39-76) + the 8-worker DataLoader of
+ * main_img_denoising.py:277-310.  image: device f32 [3, H, W] (already normalised).  boxes_host: HOST int32 [V, 4] =
+ * (top, left, height, width) of every crop, flips_host: HOST int32 [V] (the caller draws them with the reference's own
+ * RNG calls).  out: device [V, 3, OH, OW] f32 or bf16 = hflip?(resized_crop(image, box, (OH, OW), BICUBIC,
+ * antialias=True)); coords_out (optional): device f32 [V, hp, wp, 2] = (x, y) of every patch inside the image.
+ * ------------------------------------------------------------------------------------------------------- */
+int dvt_view_crops(const float* image, int H, int W, const int* boxes_host, const int* flips_host, int V, void* out,
+                   int out_dtype, int OH, int OW, float* coords_out, int hp, int wp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

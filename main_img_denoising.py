@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "denoising-vit_b200"))
 
 import dvt.models as DVT  # noqa: E402
 import dvt.utils.misc as misc  # noqa: E402
-from dvt.dataset import RandomResizedCropFlip, SingleImageDataset  # noqa: E402
+from dvt.dataset import GpuViewGenerator, RandomResizedCropFlip, SingleImageDataset  # noqa: E402
 from dvt.fit import make_patch_coordinates  # noqa: E402
 from dvt.stage1 import Stage1Config, Stage1Pipeline  # noqa: E402
 
@@ -80,6 +80,9 @@ def get_args(argv=None):
     p.add_argument("--num_vis_samples", type=int, default=5)
     p.add_argument("--vis_freq", type=int, default=100)
     p.add_argument("--seed", type=int, default=0)
+    # B200 extension (not a reference flag): where the augmented views are produced
+    p.add_argument("--view_backend", type=str, default="gpu", choices=["gpu", "cpu"],
+                   help="gpu: one dvt_view_crops launch per image; cpu: the reference's DataLoader of CPU transforms")
     args = p.parse_args(argv)
     assert os.path.exists(args.img_path), f"Image not found: {args.img_path}"
     if isinstance(args.input_size, int):
@@ -122,7 +125,12 @@ def main(args):
 
     num_samples = args.num_views + 1  # + the un-augmented image
     coords = torch.zeros((num_samples, pipe.h, pipe.w, 2), dtype=torch.float32, device=device)
-    views = torch.zeros((num_samples, 3) + args.input_size, dtype=host_dtype).pin_memory()
+    if args.view_backend == "gpu":
+        views, views_dev = None, torch.empty((num_samples, 3) + args.input_size, dtype=host_dtype, device=device)
+        view_gen = GpuViewGenerator(args.input_size, num_views=args.num_views, scale=(0.1, 0.5), patch_size=vit.patch_size,
+                                    stride=args.stride_size, dtype=host_dtype)
+    else:
+        views = torch.zeros((num_samples, 3) + args.input_size, dtype=host_dtype).pin_memory()
     dataset = SingleImageDataset(
         size=args.input_size,
         base_transform=transforms.Compose([transforms.ToPILImage(), transforms.Resize(args.input_size),
@@ -140,15 +148,21 @@ def main(args):
                 print(f"Skipping {filename}")
                 continue
         dataset.set_image(filename)
-        loader = torch.utils.data.DataLoader(dataset, args.extract_bsz, num_workers=8)
         t0 = time.time()
-        for i, data in enumerate(loader):
-            s = slice(i * args.extract_bsz, i * args.extract_bsz + data["transformed_view"].shape[0])
-            views[s] = data["transformed_view"].to(host_dtype)
-            coords[s] = data["pixel_coords"].to(device)
-        views[-1] = data["full_image"][0].to(host_dtype)
-        coords[-1] = make_patch_coordinates(pipe.h, pipe.w, start=0, end=1)
-        bank = pipe.extract_bank(views)
+        if args.view_backend == "gpu":
+            # one kernel launch for all views (dvt_view_crops); the host only draws the crop boxes / flips, with the
+            # reference's own RNG calls (dvt/dataset/gpu_views.py)
+            gpu_views, gpu_coords = view_gen(dataset.image.to(device, torch.float32), views_out=views_dev, coords_out=coords)
+            bank = pipe.extract_bank(gpu_views)
+        else:
+            loader = torch.utils.data.DataLoader(dataset, args.extract_bsz, num_workers=8)
+            for i, data in enumerate(loader):
+                s = slice(i * args.extract_bsz, i * args.extract_bsz + data["transformed_view"].shape[0])
+                views[s] = data["transformed_view"].to(host_dtype)
+                coords[s] = data["pixel_coords"].to(device)
+            views[-1] = data["full_image"][0].to(host_dtype)
+            coords[-1] = make_patch_coordinates(pipe.h, pipe.w, start=0, end=1)
+            bank = pipe.extract_bank(views)
         torch.cuda.synchronize()
         t1 = time.time()
         print(f"Feature extraction time: {t1 - t0:.2f}s")
