@@ -96,14 +96,13 @@ def kernel_rooflines(pipe, extract_bsz, dev):
              lambda: ops.gemm_tn(xn, w_fc1, b_fc1, "gelu", torch.bfloat16),
              lambda: ops.gemm_tn_residual_(x, hid, w_fc2, b_fc2, gam)]
 
-    def time_alone(fn, reps=10, warm=3, flush_l2=True):
+    def time_alone(fn, reps=10, warm=3):
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
-            if flush_l2:
-                flush.zero_()
+            flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -115,10 +114,24 @@ def kernel_rooflines(pipe, extract_bsz, dev):
     gemm_ms = [time_alone(fn) for fn in gemms]
     gemm_flops = Bv * (4.85e9 + 1.62e9 + 12.93e9)
     sweep_ctas = int(os.environ.get("DVT_FIT_SWEEP_CTAS", "40").split(",")[0])  # geometry of the timed region (fit.cu default)
-    # one event pair per launch, no flush: the sweep streams 474 MB per launch, far more than the L2 holds
-    sweep_ms = time_alone(lambda: pipe.engine.sweep_once(max(sweep_ctas, 0)), flush_l2=False)
-    sweep_full_ms = time_alone(lambda: pipe.engine.sweep_once(0), flush_l2=False)
     del flush
+
+    def time_stream(fn, reps=20, warm=3):
+        """20 back-to-back launches between one event pair (the queue stays full, so host launch latency is not in the
+        figure); no flush: the sweep streams 474 MB per launch, far more than the L2 holds."""
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    sweep_ms = time_stream(lambda: pipe.engine.sweep_once(max(sweep_ctas, 0)))
+    sweep_full_ms = time_stream(lambda: pipe.engine.sweep_once(0))
     sweep_bytes = 24.0 * pipe.field.neural_field.params.numel()
     gbs = lambda ms: sweep_bytes / (ms / 1e3) / 1e9  # noqa: E731
     return {"gemm_ms": gemm_ms, "gemm_tflops": gemm_flops / (sum(gemm_ms) / 1e3) / 1e12, "gemm_flops": gemm_flops,
@@ -430,7 +443,7 @@ def main():
                     "full_grid": {"ms_per_launch": kr["sweep_full_ms"], "achieved": kr["sweep_full_gbs"],
                                   "frac": kr["sweep_full_gbs"] / pk["hbm_gbs"],
                                   "note": "same kernel on 8 x #SM CTAs of 256 threads (the sequential schedule's geometry)"},
-                    "timed": "alone, one CUDA-event pair per launch, 10 launches (474 MB per launch >> L2)",
+                    "timed": "alone, CUDA events around 20 back-to-back launches (474 MB per launch >> L2)",
                     "peak_source": pk["source"] + " (copy bandwidth)"}
         # path level, from the CUDA-event spans INSIDE the timed region (the two paths of neighbouring images overlap,
         # so each span is stretched by the other path's share of the SMs / HBM)
