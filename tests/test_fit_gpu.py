@@ -302,3 +302,63 @@ def test_fit_engine_reuse_with_another_bank():
     assert _min_cos(qa.cpu(), qb.cpu()) > 0.9999
     assert _min_cos(qa.cpu(), torch.from_numpy(z["denoised_feats"])) > 0.999
     assert np.allclose(used.losses(), fresh.losses(), rtol=1e-3, atol=1e-5)
+
+
+# ---- headline problem size (BASELINE.json configs[2]: C 768, 37 x 37 noise map, 16 levels incl. the hashed one,
+# ---- 2048 pixels per step); small synthetic bank so that the CPU oracle finishes in seconds ----------------------
+_FULL = dict(C=768, h=37, w=37, V=4, bsz=2048, n_levels=16, lr=0.01, min_lr=0.001, weight_decay=1e-5, freeze_after=0.5,
+             loss_scale=1024.0, seed=11)
+
+
+def test_fit_full_size_first_steps_match_oracle():
+    """Six optimisation steps at the headline size against the CPU oracle (three per phase): logged losses within 1e-3
+    relative, every parameter group moves along the oracle's update."""
+    from dvt.fit import FitEngine
+    from oracle import fit as OF
+    cfg = dict(_FULL, num_iters=6, warmup_iters=2)
+    feats, coords, init, idx, den, field, ometa = _setup(cfg)
+    ora = OF.fit(feats, coords, cfg["h"], cfg["w"], ometa, init, idx, lr=cfg["lr"], min_lr=cfg["min_lr"],
+                 weight_decay=cfg["weight_decay"], warmup_iters=cfg["warmup_iters"], freeze_after=cfg["freeze_after"],
+                 loss_scale=cfg["loss_scale"], log_every=1)
+    eng = FitEngine(cfg["C"], cfg["h"], cfg["w"], cfg["bsz"], field.meta)
+    eng.fit(den, field, feats.reshape(-1, cfg["C"]).cuda().contiguous(), coords.reshape(-1, 2).cuda().contiguous(), idx,
+            graph_steps=2, lr=cfg["lr"], min_lr=cfg["min_lr"], warmup_iters=cfg["warmup_iters"],
+            freeze_after=cfg["freeze_after"], weight_decay=cfg["weight_decay"], loss_scale=cfg["loss_scale"])
+    torch.cuda.synchronize()
+    assert _L().device_error() == 0
+    losses = eng.losses()
+    for row in ora["logs"]:
+        s = int(row[0])
+        for j in range(5):
+            assert abs(losses[s, j] - row[1 + j]) <= 1e-3 * abs(row[1 + j]) + 1e-6, f"step {s} loss[{j}] {losses[s, j]} vs {row[1 + j]}"
+    for k in ("table", "G", "mlp.0.weight", "mlp.2.weight", "res.0.weight", "res.4.weight"):
+        got = eng.get_param(k, init[k]).cpu() - init[k]
+        ref = ora["params"][k] - init[k]
+        moved = ref.abs() > 0
+        cos = F.cosine_similarity(got[moved].flatten().double(), ref[moved].flatten().double(), dim=0).item()
+        assert cos > 0.99, f"{k}: update cosine {cos} at the headline size"
+
+
+def test_fit_full_size_schedules_agree(monkeypatch):
+    """Size-independent property at the headline size: the software-pipelined schedule (default) and the sequential one
+    are the same computation -- 80 steps across the phase boundary give the same table and the same loss trajectory."""
+    from dvt.fit import FitEngine
+    cfg = dict(_FULL, num_iters=80, warmup_iters=8)
+    outs = []
+    for pipeline in ("0", "1"):
+        monkeypatch.setenv("DVT_FIT_PIPELINE", pipeline)
+        feats, coords, init, idx, den, field, _ = _setup(cfg)
+        eng = FitEngine(cfg["C"], cfg["h"], cfg["w"], cfg["bsz"], field.meta)
+        eng.fit(den, field, feats.reshape(-1, cfg["C"]).cuda().contiguous(), coords.reshape(-1, 2).cuda().contiguous(), idx,
+                graph_steps=20, lr=cfg["lr"], min_lr=cfg["min_lr"], warmup_iters=cfg["warmup_iters"],
+                freeze_after=cfg["freeze_after"], weight_decay=cfg["weight_decay"], loss_scale=cfg["loss_scale"])
+        torch.cuda.synchronize()
+        assert _L().device_error() == 0
+        outs.append((eng.get_param("table", init["table"]).cpu() - init["table"], eng.losses().copy(),
+                     eng.query(coords[-1:].cuda()).cpu()))
+    (ta, la, qa), (tb, lb, qb) = outs
+    cos = F.cosine_similarity(ta.flatten().double(), tb.flatten().double(), dim=0).item()
+    assert cos > 0.9999, f"table update cosine between schedules {cos}"
+    assert np.allclose(la, lb, rtol=2e-3, atol=1e-5)
+    assert _min_cos(qa, qb) > 0.9999
+    assert la[-1, 0] < la[8, 0], "the loss must fall over the run"
