@@ -41,7 +41,8 @@ constexpr int ATT_OFF_P = ATT_OFF_V + 2 * ATT_TILE_BYTES;      // 1 buffer x 2 k
 constexpr int ATT_OFF_BAR = ATT_OFF_P + 2 * ATT_TILE_BYTES;
 constexpr int ATT_NUM_BARS = 1 + 1 + 1 + 2 + 2 + 1 + 1 + 1 + 2;
 constexpr int ATT_OFF_TMEM = ATT_OFF_BAR + ATT_NUM_BARS * 8;
-constexpr int ATT_SMEM_TOTAL = ATT_OFF_TMEM + 16 + 1024;
+constexpr int ATT_OFF_XCH = ATT_OFF_TMEM + 16;                 // PAIR mode: row-max / row-sum exchange, [2 parity][2 half][128]
+constexpr int ATT_SMEM_TOTAL = ATT_OFF_XCH + 2 * 2 * 128 * 4 + 1024;
 // TMEM columns: S [0,128) O0 [128,192) O1 [192,256)
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t ATT_TM_S = 0, ATT_TM_O = 128;
@@ -52,10 +53,33 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <bool LAZY>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// MODE 0: O accumulated in registers.  MODE 1 (LAZY): O in TMEM, lazy rescaling, one softmax thread per query row.
+// MODE 2 (LAZY + PAIR): as MODE 1 with TWO threads per query row (8 softmax warps: warp w and w + 4 share a TMEM lane
+// quadrant and take 64 of the 128 keys of a tile each; row maxima / sums are exchanged through shared memory) -- twice
+// the warps per scheduler to hide the ALU / MUFU / TMEM latencies the single thread per row exposes.
+// exp2 on the FMA / ALU pipes (range reduction by the 1.5 * 2^23 trick + degree-4 polynomial of 2^f on [-0.5, 0.5],
+// relative error 4e-5 -- P is rounded to bf16 (4e-3) right after): the MUFU (XU) pipe is the busiest unit of this kernel
+// (ncu: 50 %), so MODE 3 evaluates one exponential in four here instead of with ex2.approx.
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -120.0f);
+  const float r = x + 12582912.0f;     // round-to-nearest integer n of x sits in the low mantissa bits of r
+  const float f = x - (r - 12582912.0f);
+  float p = 0.0096181291f;
+  p = fmaf(p, f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));   // p * 2^n
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 320 : ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int C,
                     float scale_log2e) {
+  constexpr bool LAZY = MODE >= 1;
+  constexpr bool PAIR = MODE == 2;
+  constexpr bool POLY = MODE == 3;   // MODE 3 = MODE 1 with a quarter of the exponentials on the FMA pipe
+  constexpr int NSOFT = PAIR ? 256 : 128;  // softmax threads
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + ATT_OFF_Q;
@@ -87,8 +111,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     mbar_init(k_full, 1);
     mbar_init(k_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_empty, NSOFT);
+    mbar_init(p_full, NSOFT);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
@@ -170,7 +194,119 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    if constexpr (LAZY) {
+    if constexpr (PAIR) {
+      const int half = (warp - 2) >> 2;   // keys [half * 64, half * 64 + 64) of every tile; O columns [half * 32, +32)
+      float* xch = reinterpret_cast<float*>(smem + ATT_OFF_XCH);
+      float m_run = -INFINITY, l_run = 0.f;  // l_run: this thread's half of the row sum
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(s_full, j & 1, 17);
+        tc_fence_after();
+        uint32_t sreg[2][32];
+        tmem_ld_32x32(lane_addr + ATT_TM_S + half * 64, sreg[0]);
+        tmem_ld_32x32(lane_addr + ATT_TM_S + half * 64 + 32, sreg[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_empty);
+        const int kbase = j * ATT_BK + half * 64;
+        const bool partial = kbase + 64 > N;
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int nval = partial ? N - kbase - c * 32 : 32;
+          if (nval >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sreg[c][i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nval) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sreg[c][i]));
+          }
+        }
+        const float m_loc = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        float* xj = xch + (j & 1) * 256;
+        xj[half * 128 + row] = m_loc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight softmax warps
+        const float m_tile = fmaxf(m_loc, xj[(half ^ 1) * 128 + row]) * scale_log2e;  // finite: >= 1 valid key per tile
+        const float m_new = fmaxf(m_run, m_tile);
+        const bool grow = m_new - m_run > 8.0f;
+        const float m_use = grow ? m_new : m_run;
+        const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int nval = partial ? N - kbase - c * 32 : 32;
+          if (nval >= 32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
+              const float p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
+              ls[i & 3] += p0 + p1;
+              sreg[c][i] = pack_bf16x2(p0, p1);       // packed in place: sreg[c][0..15]
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p0 = 0.f, p1 = 0.f;
+              if (2 * i < nval) p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
+              if (2 * i + 1 < nval) p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
+              ls[i & 3] += p0 + p1;
+              sreg[c][i] = pack_bf16x2(p0, p1);
+            }
+          }
+        }
+        if (j > 0) {
+          mbar_wait(&o_full[0], (j - 1) & 1, 18);  // PV_{j-1} done: P buffer and O are free
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {       // same rows, hence same decision, in both warps of the pair
+            uint32_t o[32];
+            tmem_ld_32x32(lane_addr + ATT_TM_O + half * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+            tmem_st_32x32(lane_addr + ATT_TM_O + half * 32, o);
+            tmem_st_wait();
+          }
+        }
+        // this thread's 64 keys = k-atom `half`, all eight 16-byte chunks of row `row`
+        uint8_t* atom = sP + half * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c * 4 + q) ^ (row & 7);
+            *reinterpret_cast<uint4*>(atom + chunk * 16) =
+                make_uint4(sreg[c][4 * q], sreg[c][4 * q + 1], sreg[c][4 * q + 2], sreg[c][4 * q + 3]);
+          }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
+        m_run = m_use;
+      }
+      mbar_wait(&o_full[0], (T - 1) & 1, 19);
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld_32x32(lane_addr + ATT_TM_O + half * 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      float* xl = xch + (T & 1) * 256;               // the buffer the last tile did not use
+      xl[half * 128 + row] = l_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float inv = 1.0f / (l_run + xl[(half ^ 1) * 128 + row]);
+      const int q = q0 + row;
+      if (q < N) {
+        __nv_bfloat16* dst = out + ((size_t)b * N + q) * C + head * ATT_D + half * 32;
+#pragma unroll
+        for (int d8 = 0; d8 < 4; ++d8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            w[i] = pack_bf16x2(__uint_as_float(o[d8 * 8 + 2 * i]) * inv, __uint_as_float(o[d8 * 8 + 2 * i + 1]) * inv);
+          *reinterpret_cast<uint4*>(dst + d8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    } else if constexpr (LAZY) {
       float m_run = -INFINITY;  // the maximum (of s * scale_log2e) this row's P / O / l are currently relative to
       float l_run = 0.f;
       for (int j = 0; j < T; ++j) {
@@ -210,8 +346,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           if (nval >= 32) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
-              const float p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
+              const float x0 = fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use);
+              const float x1 = fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use);
+              const float p0 = ex2(x0);
+              const float p1 = (POLY && (i & 1)) ? ex2_fma(x1) : ex2(x1);
               l_tile += p0 + p1;
               packed[c][i] = pack_bf16x2(p0, p1);
             }
@@ -475,12 +613,15 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     return DVT_OK;
   }
   static bool attr_set = false;  // (attention is never launched inside a stream capture)
-  static bool lazy = true;
+  static int mode = 1;  // DVT_ATTN_MODE: 0 O in registers, 1 lazy rescaling (default), 2 lazy + two threads per row,
+                        // 3 lazy + a quarter of the exponentials on the FMA pipe
   if (!attr_set) {
-    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
-    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
-    const char* v = getenv("DVT_ATTN_LAZY");
-    lazy = !(v && v[0] == '0');
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    const char* v = getenv("DVT_ATTN_MODE");
+    if (v && v[0] >= '0' && v[0] <= '3') mode = v[0] - '0';
     attr_set = true;
   }
   CUtensorMap tm;
@@ -489,8 +630,10 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   if (rc) return rc;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
   const float sl2 = scale * 1.4426950408889634f;
-  if (lazy) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<true>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
-  else DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<false>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
+  if (mode == 3) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
+  else if (mode == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<2>, grid, dim3(320), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
+  else if (mode == 1) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<1>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
+  else DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<0>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;

@@ -5,18 +5,19 @@
 // dense Adam sweep, loss scale never unscaled, per-parameter step counters, G frozen / residual MLP started after
 // `freeze_step`).
 //
-// One step = a fixed sequence of kernels on one stream (captured into CUDA graphs of several steps by the host):
-//   encode (index -> coords -> hash-grid gather/interp -> bf16)            [+ phase 2: gather raw rows -> bf16]
-//   GEMM  h1 = relu(enc W1^T + b1)        GEMM  F = h1 W2^T + b2            [+ residual MLP forward, 3 GEMMs]
-//   loss  (pred = F + G[r,c] (+R), MSE + cosine, d pred, dG atomics, loss log) [+ residual losses, dR]
-//   GEMM  dh1 = (dpred W2) * relu'        GEMM  dW2|db2 += dpred^T [h1|1]   GEMM dW1|db1 += dh1^T [enc|1]
-//   GEMM  denc = dh1 W1                   grid backward (vector atomics into the dense table gradient)
-//   [+ residual MLP backward, 5 GEMMs]    Adam(table) dense sweep           Adam(small params) + bf16 mirrors
+// One step = a fixed set of kernels on five streams (captured into CUDA graphs of several steps by the host; the full
+// schedule with its hazards is documented at fit_enqueue_step):
+//   main  : GEMM h1 = relu(enc W1^T + b1), GEMM F = h1 W2^T + b2, loss (pred = F + G[r,c] (+R), MSE + cosine, d pred,
+//           dG atomics, loss log), dgrad, dgrad, grid backward (vector atomics + touched-entry stamps),
+//           encode of the NEXT step (hash-grid gather / interpolation with the pending Adam steps applied on the fly)
+//   sides : gather of the sampled bank rows, residual MLP forward (3 GEMM) / backward (5 GEMM), weight-gradient GEMMs,
+//           Adam(small params), and the dense Adam sweep of the hash table (software-pipelined two steps deep)
 // All GEMMs run on tcgen05 (gemm.cu) as 3xTF32 products of fp32 hi/lo planes (fp32-accurate: bf16 operands cannot
 // hold the cosine >= 0.999 parity bar); weight-gradient GEMMs read the activations as MN-major
 // operands, so no transposed copies exist; bias gradients come from a ones column appended to the activation buffers.
 //
-// HBM layout: table p/m/v/g as four fp32 arrays of n_entries*8; "small" params (field MLP, G as [h*w, C],
+// HBM layout: table p/m/v as two ping-pong copies of three fp32 arrays of n_entries*8, gradients as a ring of three
+// such arrays with per-entry step stamps; "small" params (field MLP, G as [h*w, C],
 // residual MLP) in one flat fp32 buffer with identically laid out m / v / grad buffers and TF32 hi/lo operand planes.
 #include "common.cuh"
 #include "gemm.cuh"

@@ -2,4 +2,4 @@ set -x
 cd $GRAFT_REPO_ROOT
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 900 python bench.py --steps 3 --warmup 3 | tail -1 > gpurun_out/bench_r1z.json; cut -c1-200 gpurun_out/bench_r1z.json
+timeout 900 python bench.py --steps 3 --warmup 3 | tail -1 > gpurun_out/bench_final.json; cut -c1-200 gpurun_out/bench_final.json
