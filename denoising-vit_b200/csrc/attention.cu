@@ -139,10 +139,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(k_empty, (j & 1) ^ 1, 10);
+        mbar_wait_relaxed(k_empty, (j & 1) ^ 1, 10);
         mbar_expect_tx(k_full, ATT_TILE_BYTES);
         tma_load_3d(sK, &tm_qkv, k_full, C + head * ATT_D, j * ATT_BK, b);
-        mbar_wait(&v_empty[st], ph ^ 1, 11);
+        mbar_wait_relaxed(&v_empty[st], ph ^ 1, 11);
         mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
         tma_load_3d(sV + st * ATT_TILE_BYTES, &tm_qkv, &v_full[st], 2 * C + head * ATT_D, j * ATT_BK, b);
       }

@@ -109,6 +109,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Bounded wait: traps (instead of hanging) when the phase never completes.
+// Wait of a role that is not latency critical (a TMA producer waiting for a free slot): backs off with nanosleep so that
+// its spin loop does not take issue slots from the math warps on the same scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (clock64() - t0 > DVT_WATCHDOG_CYCLES) dev_fail(0xDEADu, tag);
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
