@@ -28,6 +28,8 @@ def main():
     hdr = rows[0]
     for r in rows[2:]:
         d = dict(zip(hdr, r))
+        if " at::" in " " + d.get("Kernel Name", ""):   # torch helper kernels of the driving script
+            continue
         lines.append(f"## launch: {d.get('Kernel Name', '?')[:150]}")
         for k in hdr:
             if k in WANT or ("inst_executed_pipe_" in k and k.endswith(".avg.pct_of_peak_sustained_active") and k.startswith("sm__")):
