@@ -70,5 +70,5 @@ def test_stage1_driver_writes_the_reference_store(tmp_path):
     assert raw.dtype == np.float32 and raw.shape == (h, w, C) and np.array_equal(raw, feats[-1].numpy())
     assert den.dtype == np.float32 and den.shape == (1, h, w, C)
     with open(raw_p, "rb") as f:
-        assert f.read(8) == b"\\x93NUMPY\\x01\\x00"          # NPY format version 1.0
+        assert f.read(8) == bytes([0x93]) + b"NUMPY" + bytes([1, 0])          # NPY format version 1.0
     assert misc.check_if_file_exists(args, img)
