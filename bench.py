@@ -309,7 +309,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     V = args.views + 1
-    vit = DVT.PretrainedViTWrapper(MODEL, stride=14)
+    vit = DVT.PretrainedViTWrapper(MODEL, stride=14, allow_random_init=True)
     with torch.no_grad():
         for b in vit.model.blocks:  # non-degenerate LayerScale (DINOv2 init 1e-5 would switch the blocks off)
             b.ls1.gamma.fill_(1.0)

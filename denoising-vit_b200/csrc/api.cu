@@ -20,12 +20,16 @@ struct Fit;
 int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const float* scale, const uint32_t* res,
                const uint32_t* size, const uint32_t* offset, const uint32_t* hashed);
 void fit_destroy(Fit* f);
-int fit_set_param(Fit* f, const char* name, const float* src, size_t numel);
+int fit_set_param(Fit* f, const char* name, const float* src, size_t numel, cudaStream_t caller);
 int fit_get_param(Fit* f, const char* name, float* dst, size_t numel);
+int fit_init_params(Fit* f, uint64_t seed, cudaStream_t caller);
 int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, const int* idx_host, int num_iters,
-              float lr, float min_lr, int warmup_iters, float freeze_after, float weight_decay, float loss_scale);
+              double lr, double min_lr, int warmup_iters, int freeze_step, double weight_decay, double loss_scale,
+              int validate, cudaStream_t caller);
+int fit_check(Fit* f);
 int fit_run(Fit* f, int count, int use_graphs, cudaStream_t st, int impl);
 int fit_losses(Fit* f, float* dst_host, int num_iters);
+int fit_losses_async(Fit* f, float* dst, int num_iters, cudaStream_t caller);
 int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, int impl);
 int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, int impl);
 int fit_sweep_once(Fit* f, int ctas, cudaStream_t st);
@@ -234,20 +238,28 @@ int dvt_fit_create(dvt_fit_t** out, int feat_dim, int gh, int gw, int bsz, int n
                     offset_host, hashed_host);
 }
 void dvt_fit_destroy(dvt_fit_t* h) { fit_destroy(reinterpret_cast<Fit*>(h)); }
-int dvt_fit_set_param(dvt_fit_t* h, const char* name, const float* src, size_t numel) {
+int dvt_fit_set_param(dvt_fit_t* h, const char* name, const float* src, size_t numel, void* stream) {
   DVT_REQUIRE(h && name && src, "dvt_fit_set_param: null argument");
-  return fit_set_param(reinterpret_cast<Fit*>(h), name, src, numel);
+  return fit_set_param(reinterpret_cast<Fit*>(h), name, src, numel, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_fit_init_params(dvt_fit_t* h, unsigned long long seed, void* stream) {
+  DVT_REQUIRE(h, "dvt_fit_init_params: null handle");
+  return fit_init_params(reinterpret_cast<Fit*>(h), (uint64_t)seed, reinterpret_cast<cudaStream_t>(stream));
 }
 int dvt_fit_get_param(dvt_fit_t* h, const char* name, float* dst, size_t numel) {
   DVT_REQUIRE(h && name && dst, "dvt_fit_get_param: null argument");
   return fit_get_param(reinterpret_cast<Fit*>(h), name, dst, numel);
 }
 int dvt_fit_begin(dvt_fit_t* h, const float* bank_feats, const float* bank_coords, size_t bank_rows,
-                  const int32_t* idx_host, int num_iters, float lr, float min_lr, int warmup_iters, float freeze_after,
-                  float weight_decay, float loss_scale) {
+                  const int32_t* idx_host, int num_iters, double lr, double min_lr, int warmup_iters, int freeze_step,
+                  double weight_decay, double loss_scale, int validate, void* stream) {
   DVT_REQUIRE(h, "dvt_fit_begin: null handle");
   return fit_begin(reinterpret_cast<Fit*>(h), bank_feats, bank_coords, bank_rows, idx_host, num_iters, lr, min_lr,
-                   warmup_iters, freeze_after, weight_decay, loss_scale);
+                   warmup_iters, freeze_step, weight_decay, loss_scale, validate, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_fit_check(dvt_fit_t* h) {
+  DVT_REQUIRE(h, "dvt_fit_check: null handle");
+  return fit_check(reinterpret_cast<Fit*>(h));
 }
 int dvt_fit_run(dvt_fit_t* h, int count, int graph_steps, void* stream) {
   DVT_REQUIRE(h, "dvt_fit_run: null handle");
@@ -256,6 +268,10 @@ int dvt_fit_run(dvt_fit_t* h, int count, int graph_steps, void* stream) {
 int dvt_fit_losses(dvt_fit_t* h, float* dst_host, int num_iters) {
   DVT_REQUIRE(h && dst_host, "dvt_fit_losses: null argument");
   return fit_losses(reinterpret_cast<Fit*>(h), dst_host, num_iters);
+}
+int dvt_fit_losses_async(dvt_fit_t* h, float* dst, int num_iters, void* stream) {
+  DVT_REQUIRE(h && dst, "dvt_fit_losses_async: null argument");
+  return fit_losses_async(reinterpret_cast<Fit*>(h), dst, num_iters, reinterpret_cast<cudaStream_t>(stream));
 }
 int dvt_fit_query(dvt_fit_t* h, const float* coords, int n, float* out, void* stream) {
   DVT_REQUIRE(h, "dvt_fit_query: null handle");

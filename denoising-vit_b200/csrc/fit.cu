@@ -74,10 +74,11 @@ __device__ __forceinline__ CornerSet grid_corners(const GridLevels& g, int l, fl
 // a launch-time constant, so kernels take (idx_all, step_base, step_off) and resolve s = *step_base + step_off on
 // the device; idx_all == nullptr means "row i" (query mode).
 // The bank / coordinate pointers of the current fit are read through a device-side record as well (FitInputs), so a
-// captured graph stays valid when the next image's bank lives in another buffer.
+// captured graph stays valid when the next image's bank / sampling stream live in another buffer.
 struct FitInputs {
   const float* bank;
   const float* coords;
+  const int* idx;  // [num_iters + 1, bsz] sampling stream of the current fit (double-buffered by the host engine)
 };
 struct StepRows {
   const int* idx_all;
@@ -88,7 +89,8 @@ struct StepRows {
   __device__ __forceinline__ const float* bank(const float* direct) const { return in ? in->bank : direct; }
   __device__ __forceinline__ int step() const { return *step_base + step_off; }
   __device__ __forceinline__ const int* rows(int n) const {
-    return idx_all ? idx_all + (size_t)step() * n : nullptr;
+    const int* base = in ? in->idx : idx_all;
+    return base ? base + (size_t)step() * n : nullptr;
   }
 };
 
@@ -150,8 +152,11 @@ fit_encode_kernel(GridLevels g, TableBufs tb, const float* __restrict__ table_fi
                   StepRows sr, int n, float* __restrict__ enc, int ld_enc, size_t plane,
                   const AdamScalars* __restrict__ sc, float wd, int npeek) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int q = t >> 2, k = t & 3;
-  if (q >= n * g.n_levels) return;  // n % 8 == 0: warps are either complete or empty
+  const int k = t & 3;
+  // Threads past the end stay in the kernel (clamped to the last element, store predicated off): the shuffles below name
+  // the full warp, and n * n_levels need not be a multiple of 8 (query mode: n = h * w).
+  const bool live = (t >> 2) < n * g.n_levels;
+  const int q = live ? (t >> 2) : n * g.n_levels - 1;
   pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
   pdl_trigger();
   const int i = q % n, l = q / n;
@@ -209,7 +214,7 @@ fit_encode_kernel(GridLevels g, TableBufs tb, const float* __restrict__ table_fi
     o[j] = (k & 2) ? a - hi : hi;
   }
   float* dst = enc + (size_t)i * ld_enc + l * FIT_F + (k & 1) * 4 + ((k & 2) ? plane : 0);
-  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  if (live) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // fp32 encode (unit-test entry point: bit-level check of indices / weights against the oracle)
@@ -612,6 +617,7 @@ __global__ void fit_coord_range_kernel(const float* __restrict__ coords, size_t 
 // ====================================================================================================
 // host engine
 // ====================================================================================================
+#define FIT_RC0(x) do { int _rc0 = (x); if (_rc0) return _rc0; } while (0)
 struct Seg {
   int off = 0, rows = 0, cols = 0;  // floats; weights are [rows, cols] row-major, biases rows x 1
 };
@@ -645,7 +651,20 @@ struct Fit {
   int ld_enc, ld_h1, ld_raw, ld_r;
   // schedule
   int num_iters = 0, freeze_step = 0;
-  int* idx = nullptr;         // [num_iters, bsz]
+  int cur_step = 0;                            // steps of the current schedule already enqueued (host mirror of *step_base)
+  // sampling stream: two device buffers + two pinned staging buffers, so that the upload of the next image's stream
+  // runs (on sU) while the current fit is still reading its own
+  int* idx[2] = {nullptr, nullptr};            // [num_iters + 1, bsz] each
+  int* idx_pinned[2] = {nullptr, nullptr};
+  size_t idx_cap = 0;                          // elements per buffer
+  int idx_slot = 1;                            // buffer of the current fit (toggled by fit_begin)
+  cudaStream_t sU = nullptr;                   // upload stream
+  cudaEvent_t ev_upload[2] = {};               // H2D of slot s complete
+  cudaEvent_t ev_run_done[2] = {};             // last fit_run that read slot s complete
+  bool run_done_valid[2] = {false, false};
+  int* flags_dev = nullptr;                    // bit 0: a coordinate outside [0, 1]; bit 1: a sampled row out of range
+  int* flags_pinned = nullptr;
+  double sched_key[6] = {-1, -1, -1, -1, -1, -1};  // (num_iters, warmup, lr, min_lr, freeze_step) of the uploaded tables
   AdamScalars *sc_main = nullptr, *sc_res = nullptr;
   float* losses = nullptr;    // [num_iters, 5]
   int* step_base = nullptr;
@@ -699,6 +718,9 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sC, cudaStreamNonBlocking, prio_hi));
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sE, cudaStreamNonBlocking, prio_hi));
   DVT_CUDA_OK(cudaStreamCreateWithPriority(&f->sD, cudaStreamNonBlocking, prio_lo));  // the sweep yields to the chain
+  DVT_CUDA_OK(cudaStreamCreateWithFlags(&f->sU, cudaStreamNonBlocking));
+  for (auto& e : f->ev_upload) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : f->ev_run_done) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : f->ev) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : f->ev_sweep) DVT_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
@@ -760,6 +782,8 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   A((void**)&f->dR, n * C * 8); A((void**)&f->dr2, n * Hr * 8); A((void**)&f->dr1, n * Hr * 8);
   A((void**)&f->Rout, n * C * 4); A((void**)&f->step_base, sizeof(int));
   A((void**)&f->inputs_dev, sizeof(FitInputs));
+  A((void**)&f->flags_dev, sizeof(int));
+  if (!rc && cudaHostAlloc((void**)&f->flags_pinned, sizeof(int), cudaHostAllocDefault) != cudaSuccess) rc = DVT_ERR_CUDA;
   if (rc) { for (void* p : f->owned) cudaFree(p); delete f; return rc; }
   // ones columns (bias gradients through the weight-gradient GEMMs)
   const int tb = 256, nb = (bsz + tb - 1) / tb;
@@ -787,12 +811,17 @@ void fit_destroy(Fit* f) {
   if (f->sC) cudaStreamDestroy(f->sC);
   if (f->sE) cudaStreamDestroy(f->sE);
   if (f->sD) cudaStreamDestroy(f->sD);
+  if (f->sU) cudaStreamDestroy(f->sU);
+  for (auto& e : f->ev_upload) if (e) cudaEventDestroy(e);
+  for (auto& e : f->ev_run_done) if (e) cudaEventDestroy(e);
   for (auto& e : f->ev) if (e) cudaEventDestroy(e);
   for (auto& e : f->ev_sweep) if (e) cudaEventDestroy(e);
   if (f->ev_in) cudaEventDestroy(f->ev_in);
   if (f->ev_out) cudaEventDestroy(f->ev_out);
   for (void* p : f->owned) cudaFree(p);
-  cudaFree(f->idx); cudaFree(f->sc_main); cudaFree(f->sc_res); cudaFree(f->losses);
+  for (int q = 0; q < 2; ++q) { cudaFree(f->idx[q]); cudaFreeHost(f->idx_pinned[q]); }
+  cudaFreeHost(f->flags_pinned);
+  cudaFree(f->sc_main); cudaFree(f->sc_res); cudaFree(f->losses);
   cudaFree(f->q_enc); cudaFree(f->q_h1); cudaFree(f->q_raw); cudaFree(f->q_r1); cudaFree(f->q_r2); cudaFree(f->q_stage);
   delete f;
 }
@@ -816,30 +845,53 @@ static int fit_stage(Fit* f, size_t floats) {
   return DVT_OK;
 }
 
-// Parameter names follow oracle/fit.py::PARAM_ORDER ("G" is the reference's shared_artifacts [1, C, h, w]).
-int fit_set_param(Fit* f, const char* name_c, const float* src, size_t numel) {
-  const std::string name(name_c);
-  if (name == "table") {
-    DVT_REQUIRE(numel == f->n_table, "fit_set_param: table has %zu elements, expected %zu", numel, f->n_table);
-    DVT_CUDA_OK(cudaDeviceSynchronize());
-    DVT_CUDA_OK(cudaMemcpy(f->tb.p[f->cur_host & 1], src, numel * 4, cudaMemcpyDefault));
-    return DVT_OK;
-  }
-  Seg* s = nullptr;
-  DVT_REQUIRE(fit_find(f, name, &s), "fit_set_param: unknown parameter %s", name_c);
-  const size_t expect = (size_t)s->rows * s->cols;
-  DVT_REQUIRE(numel == expect, "fit_set_param: %s has %zu elements, expected %zu", name_c, numel, expect);
-  if (name == "G") {  // [C, h*w] -> [h*w, C]
-    int rc = fit_stage(f, numel);
-    if (rc) return rc;
-    DVT_CUDA_OK(cudaMemcpy(f->q_stage, src, numel * 4, cudaMemcpyDefault));
-    fit_transpose_kernel<<<256, 256>>>(f->q_stage, f->sp + s->off, f->C, f->hw);
-    DVT_CUDA_OK(cudaGetLastError());
-    DVT_CUDA_OK(cudaDeviceSynchronize());
-  } else {
-    DVT_CUDA_OK(cudaMemcpy(f->sp + s->off, src, numel * 4, cudaMemcpyDefault));
-  }
+// ----------------------------------------------------------------------------------------------------
+// Stream discipline of the host engine.  Every call that MUTATES engine state (init / set_param / begin / run) first makes
+// the engine's main stream wait for the caller's stream and enqueues its device work on the engine's stream; every call
+// that READS state on the caller's stream (query / residual / losses / get_param) first makes the caller's stream wait for
+// the engine's.  Nothing in between synchronises the host with the device, so a driver can enqueue image i+1 while image
+// i is still being fitted (Stage1Pipeline.run_images).
+// ----------------------------------------------------------------------------------------------------
+static int fit_after_caller(Fit* f, cudaStream_t caller) {
+  DVT_CUDA_OK(cudaEventRecord(f->ev_in, caller));
+  DVT_CUDA_OK(cudaStreamWaitEvent(f->stream, f->ev_in, 0));
   return DVT_OK;
+}
+static int fit_before_caller(Fit* f, cudaStream_t caller) {
+  DVT_CUDA_OK(cudaEventRecord(f->ev_out, f->stream));
+  DVT_CUDA_OK(cudaStreamWaitEvent(caller, f->ev_out, 0));
+  return DVT_OK;
+}
+
+// Parameter names follow oracle/fit.py::PARAM_ORDER ("G" is the reference's shared_artifacts [1, C, h, w]).
+// src: host or device memory.  Device sources may be temporaries of the caller's stream-ordered allocator: the caller's
+// stream is made to wait for the copy, so the memory is not reused before it has been read.
+int fit_set_param(Fit* f, const char* name_c, const float* src, size_t numel, cudaStream_t caller) {
+  const std::string name(name_c);
+  Seg* s = nullptr;
+  if (name != "table") {
+    DVT_REQUIRE(fit_find(f, name, &s), "fit_set_param: unknown parameter %s", name_c);
+    const size_t expect = (size_t)s->rows * s->cols;
+    DVT_REQUIRE(numel == expect, "fit_set_param: %s has %zu elements, expected %zu", name_c, numel, expect);
+  } else {
+    DVT_REQUIRE(numel == f->n_table, "fit_set_param: table has %zu elements, expected %zu", numel, f->n_table);
+  }
+  int rc = fit_after_caller(f, caller);
+  if (rc) return rc;
+  cudaStream_t st = f->stream;
+  if (name == "table") {
+    DVT_CUDA_OK(cudaMemcpyAsync(f->tb.p[f->cur_host & 1], src, numel * 4, cudaMemcpyDefault, st));
+  } else if (name == "G") {  // [C, h*w] -> [h*w, C]
+    if (f->q_stage_cap < numel) DVT_CUDA_OK(cudaStreamSynchronize(st));  // the staging buffer is about to be replaced
+    rc = fit_stage(f, numel);
+    if (rc) return rc;
+    DVT_CUDA_OK(cudaMemcpyAsync(f->q_stage, src, numel * 4, cudaMemcpyDefault, st));
+    fit_transpose_kernel<<<256, 256, 0, st>>>(f->q_stage, f->sp + s->off, f->C, f->hw);
+    DVT_CUDA_OK(cudaGetLastError());
+  } else {
+    DVT_CUDA_OK(cudaMemcpyAsync(f->sp + s->off, src, numel * 4, cudaMemcpyDefault, st));
+  }
+  return fit_before_caller(f, caller);
 }
 
 int fit_get_param(Fit* f, const char* name_c, float* dst, size_t numel) {
@@ -865,85 +917,211 @@ int fit_get_param(Fit* f, const char* name_c, float* dst, size_t numel) {
   return DVT_OK;
 }
 
-// Zeroes optimiser state / gradients, rebuilds the bf16 mirrors and installs the schedule of one fit.
-// idx_host: int32 [num_iters, bsz] bank rows (the np.random.randint stream, main_img_denoising.py:73).
-int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, const int* idx_host, int num_iters,
-              float lr, float min_lr, int warmup_iters, float freeze_after, float weight_decay, float loss_scale) {
-  DVT_REQUIRE(bank && coords && idx_host && num_iters > 0, "fit_begin: bad arguments");
-  DVT_REQUIRE(bank_rows % (size_t)f->hw == 0, "fit_begin: bank rows %zu not a multiple of h*w = %d", bank_rows, f->hw);
-  f->bank = bank; f->coords = coords; f->bank_rows = bank_rows;
-  {
-    const FitInputs in{bank, coords};
-    DVT_CUDA_OK(cudaMemcpy(f->inputs_dev, &in, sizeof(in), cudaMemcpyHostToDevice));
-  }
-  // scalars that are baked into captured kernel nodes
-  if (f->wd != weight_decay || f->loss_scale != loss_scale) fit_drop_graphs(f);
-  f->wd = weight_decay; f->loss_scale = loss_scale;
-  // coordinates must lie in [0, 1] (assert of neural_feature_field.py:47, checked once per bank instead of per step)
-  int* bad = nullptr;
-  DVT_CUDA_OK(cudaMalloc(&bad, 4));
-  DVT_CUDA_OK(cudaMemset(bad, 0, 4));
-  fit_coord_range_kernel<<<256, 256>>>(coords, bank_rows * 2, bad);
-  int bad_h = 0;
-  DVT_CUDA_OK(cudaMemcpy(&bad_h, bad, 4, cudaMemcpyDeviceToHost));
-  cudaFree(bad);
-  DVT_REQUIRE(bad_h == 0, "coordinates should be in [0, 1]");
-  for (size_t i = 0; i < (size_t)num_iters * f->bsz; ++i)
-    DVT_REQUIRE(idx_host[i] >= 0 && (size_t)idx_host[i] < bank_rows, "fit_begin: index %d out of range at %zu",
-                idx_host[i], i);
-  if (num_iters != f->num_iters) {
-    cudaFree(f->idx); cudaFree(f->sc_main); cudaFree(f->sc_res); cudaFree(f->losses);
-    f->idx = nullptr; f->sc_main = f->sc_res = nullptr; f->losses = nullptr;
-    DVT_CUDA_OK(cudaMalloc(&f->idx, (size_t)(num_iters + 1) * f->bsz * 4));
-    DVT_CUDA_OK(cudaMalloc(&f->sc_main, (size_t)(num_iters + 1) * sizeof(AdamScalars)));
-    DVT_CUDA_OK(cudaMalloc(&f->sc_res, (size_t)num_iters * sizeof(AdamScalars)));
-    DVT_CUDA_OK(cudaMalloc(&f->losses, (size_t)num_iters * 5 * 4));
-    fit_drop_graphs(f);
-  }
-  const int freeze_step = (int)(freeze_after * num_iters);  // int(args.freeze_shared_artifacts_after * num_iters)
-  if (freeze_step != f->freeze_step) fit_drop_graphs(f);
-  f->num_iters = num_iters; f->freeze_step = freeze_step;
-  DVT_CUDA_OK(cudaMemcpy(f->idx, idx_host, (size_t)num_iters * f->bsz * 4, cudaMemcpyHostToDevice));
-  DVT_CUDA_OK(cudaMemset(f->idx + (size_t)num_iters * f->bsz, 0, (size_t)f->bsz * 4));
-  // the Adam scalar tables also get read one past the end by the (unused) encode of step num_iters - handled by
-  // clamping below: allocate one extra element
-
-  std::vector<AdamScalars> a(num_iters), b(num_iters);
-  for (int s = 0; s < num_iters; ++s) {
-    double lrs;  // dvt/utils/misc.py:306-322
-    if (s < warmup_iters) lrs = (double)lr * s / warmup_iters;
-    else lrs = min_lr + ((double)lr - min_lr) * 0.5 * (1.0 + cos(M_PI * (s - warmup_iters) / (double)(num_iters - warmup_iters)));
-    const int t = s + 1;
-    a[s].step_size = (float)(lrs / (1.0 - pow(0.9, t)));
-    a[s].inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(0.99, t)));
-    const int tr = s - freeze_step;  // residual MLP: first update at s = freeze_step + 1 has t = 1
-    if (tr >= 1) {
-      b[s].step_size = (float)(lrs / (1.0 - pow(0.9, tr)));
-      b[s].inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(0.99, tr)));
+// ---- device-side (re-)initialisation of all parameters: what constructing fresh SingleImageDenoiser /
+// NeuralFeatureField modules does in the reference for every image (main_img_denoising.py:39-47), without a host round
+// trip.  Counter-based generator: element e of tensor `tid` under `seed` is a pure function of (seed, tid, e).
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t seed, uint32_t tid, uint64_t e, uint32_t draw) {
+  const uint64_t h = mix64(mix64(seed + 0x9E3779B97F4A7C15ull * (tid + 1)) ^ (e * 2 + draw + 0x632BE59BD9B4E019ull));
+  return (float)((h >> 40) + 1) * (1.0f / 16777217.0f);  // (0, 1)
+}
+// kind 0: U(-bound, bound); kind 1: N(0, 1) * bound (Box-Muller); kind 2: U(-bound, bound) stored transposed: element
+// e = c * cols + r of a [rows?]... (G is drawn in the reference's [C, h*w] order and stored [h*w, C])
+__global__ void fit_init_kernel(float* __restrict__ dst, size_t n, uint64_t seed, uint32_t tid, int kind, float bound,
+                                int t_rows, int t_cols) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    float val;
+    if (kind == 1) {
+      const float u1 = u01(seed, tid, e, 0), u2 = u01(seed, tid, e, 1);
+      val = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2) * bound;
     } else {
-      b[s].step_size = 0.f; b[s].inv_bc2_sqrt = 1.f;
+      val = (2.0f * u01(seed, tid, e, 0) - 1.0f) * bound;
+    }
+    size_t o = e;
+    if (t_rows > 0) {  // e indexes [t_rows, t_cols]; stored transposed
+      const size_t r = e / t_cols, c = e - r * t_cols;
+      o = c * t_rows + r;
+    }
+    dst[o] = val;
+  }
+}
+
+// Fresh parameters for the next fit: hash table U(-1e-4, 1e-4) (tcnn's default grid initialisation), nn.Linear default
+// initialisation U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for all MLP weights and biases, G = randn * 0.02
+// (offline_denoiser.py:33-36).  The reference's own streams (tcnn pcg32, torch's Philox) are not reproduced -- no test of
+// the reference pins them -- but the distributions are.
+int fit_init_params(Fit* f, uint64_t seed, cudaStream_t caller) {
+  int rc = fit_after_caller(f, caller);
+  if (rc) return rc;
+  cudaStream_t st = f->stream;
+  auto launch = [&](float* dst, size_t n, uint32_t tid, int kind, float bound, int tr = 0, int tc = 0) -> int {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)num_sms() * 8);
+    fit_init_kernel<<<blocks, 256, 0, st>>>(dst, n, seed, tid, kind, bound, tr, tc);
+    DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return DVT_OK;
+  };
+  f->cur_host = 0;
+  FIT_RC0(launch(f->tb.p[0], f->n_table, 0, 0, 1e-4f));
+  struct { Seg* w; Seg* b; uint32_t tid; } lin[] = {{&f->W1, &f->b1, 1}, {&f->W2, &f->b2, 3}, {&f->R1, &f->rb1, 5},
+                                                    {&f->R2, &f->rb2, 7}, {&f->R3, &f->rb3, 9}};
+  for (auto& l : lin) {
+    const float bound = 1.0f / sqrtf((float)l.w->cols);
+    FIT_RC0(launch(f->sp + l.w->off, (size_t)l.w->rows * l.w->cols, l.tid, 0, bound));
+    FIT_RC0(launch(f->sp + l.b->off, (size_t)l.b->rows, l.tid + 1, 0, bound));
+  }
+  FIT_RC0(launch(f->sp + f->G.off, (size_t)f->hw * f->C, 11, 1, 0.02f, f->C, f->hw));
+  return fit_before_caller(f, caller);
+}
+
+// clamps out-of-range sampled rows (so that no kernel can read outside the bank) and records what it saw
+__global__ void fit_check_inputs_kernel(const float* __restrict__ coords, size_t n2, int* __restrict__ idx, size_t n_idx,
+                                        int bank_rows, int* __restrict__ flags) {
+  int bad = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += stride) {
+    const float c = coords[e];
+    if (!(c >= 0.f && c <= 1.f)) bad |= 1;
+  }
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_idx; e += stride) {
+    const int v = idx[e];
+    if (v < 0 || v >= bank_rows) {
+      bad |= 2;
+      idx[e] = min(max(v, 0), bank_rows - 1);
     }
   }
-  DVT_CUDA_OK(cudaMemcpy(f->sc_main, a.data(), a.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
-  DVT_CUDA_OK(cudaMemcpy(f->sc_res, b.data(), b.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
-  DVT_CUDA_OK(cudaMemset(f->losses, 0, (size_t)num_iters * 5 * 4));
-  DVT_CUDA_OK(cudaMemset(f->step_base, 0, 4));
-  DVT_CUDA_OK(cudaDeviceSynchronize());
+  if (bad) atomicOr(flags, bad);
+}
+
+__global__ void fit_set_inputs_kernel(FitInputs* dst, const float* bank, const float* coords, const int* idx,
+                                      int* step_base) {
+  dst->bank = bank;
+  dst->coords = coords;
+  dst->idx = idx;
+  *step_base = 0;
+}
+
+static int fit_flags_to_error(int flags) {
+  DVT_REQUIRE((flags & 1) == 0, "coordinates should be in [0, 1]");
+  DVT_REQUIRE((flags & 2) == 0, "fit_begin: a sampled bank row is out of range");
+  return DVT_OK;
+}
+
+// Reads the input-validation flags of the fits begun since the last check (blocks until the engine's stream is idle).
+int fit_check(Fit* f) {
+  DVT_CUDA_OK(cudaMemcpyAsync(f->flags_pinned, f->flags_dev, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+  DVT_CUDA_OK(cudaMemsetAsync(f->flags_dev, 0, sizeof(int), f->stream));
+  DVT_CUDA_OK(cudaStreamSynchronize(f->stream));
+  return fit_flags_to_error(*f->flags_pinned);
+}
+
+// Starts a fit: zeroes the optimiser state / gradients, rebuilds the TF32 operand planes of the weights and installs the
+// bank, the sampling stream and the schedule.  Everything is enqueued; nothing waits for the device unless `validate`
+// (then the range checks are read back and reported here, like the reference's assert, neural_feature_field.py:47).
+// idx_host: int32 [num_iters, bsz] bank rows (the np.random.randint stream, main_img_denoising.py:73).
+int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, const int* idx_host, int num_iters,
+              double lr, double min_lr, int warmup_iters, int freeze_step, double weight_decay, double loss_scale,
+              int validate, cudaStream_t caller) {
+  DVT_REQUIRE(bank && coords && idx_host && num_iters > 0, "fit_begin: bad arguments");
+  DVT_REQUIRE(bank_rows % (size_t)f->hw == 0, "fit_begin: bank rows %zu not a multiple of h*w = %d", bank_rows, f->hw);
+  DVT_REQUIRE(bank_rows < (size_t)1 << 31, "fit_begin: bank of %zu rows exceeds the int32 row index", bank_rows);
+  DVT_REQUIRE(freeze_step >= 0, "fit_begin: negative freeze step");
+  f->bank = bank; f->coords = coords; f->bank_rows = bank_rows;
+  // scalars that are baked into captured kernel nodes
+  if (f->wd != (float)weight_decay || f->loss_scale != (float)loss_scale || freeze_step != f->freeze_step) {
+    DVT_CUDA_OK(cudaStreamSynchronize(f->stream));
+    fit_drop_graphs(f);
+  }
+  f->wd = (float)weight_decay; f->loss_scale = (float)loss_scale;
+  const size_t n_idx = (size_t)num_iters * f->bsz;
+  // ---- rare path: buffers sized by the schedule length ----
+  if (n_idx + f->bsz > f->idx_cap) {
+    DVT_CUDA_OK(cudaDeviceSynchronize());
+    for (int q = 0; q < 2; ++q) {
+      cudaFree(f->idx[q]); cudaFreeHost(f->idx_pinned[q]);
+      f->idx[q] = nullptr; f->idx_pinned[q] = nullptr;
+      DVT_CUDA_OK(cudaMalloc(&f->idx[q], (n_idx + f->bsz) * 4));
+      DVT_CUDA_OK(cudaHostAlloc((void**)&f->idx_pinned[q], n_idx * 4, cudaHostAllocDefault));
+      f->run_done_valid[q] = false;
+    }
+    f->idx_cap = n_idx + f->bsz;
+  }
+  if (num_iters != f->num_iters) {
+    DVT_CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(f->sc_main); cudaFree(f->sc_res); cudaFree(f->losses);
+    f->sc_main = f->sc_res = nullptr; f->losses = nullptr;
+    DVT_CUDA_OK(cudaMalloc(&f->sc_main, (size_t)(num_iters + 1) * sizeof(AdamScalars)));
+    DVT_CUDA_OK(cudaMalloc(&f->sc_res, (size_t)(num_iters + 1) * sizeof(AdamScalars)));
+    DVT_CUDA_OK(cudaMalloc(&f->losses, (size_t)num_iters * 5 * 4));
+    f->sched_key[0] = -1;
+    fit_drop_graphs(f);
+  }
+  f->num_iters = num_iters; f->freeze_step = freeze_step; f->cur_step = 0;
+  // ---- sampling stream: staged through pinned memory and copied on the upload stream, beside the running fit ----
+  const int slot = f->idx_slot ^ 1;
+  f->idx_slot = slot;
+  DVT_CUDA_OK(cudaEventSynchronize(f->ev_upload[slot]));  // the copy that last read this staging buffer (long done)
+  memcpy(f->idx_pinned[slot], idx_host, n_idx * 4);
+  if (f->run_done_valid[slot]) DVT_CUDA_OK(cudaStreamWaitEvent(f->sU, f->ev_run_done[slot], 0));  // its last reader
+  DVT_CUDA_OK(cudaMemcpyAsync(f->idx[slot], f->idx_pinned[slot], n_idx * 4, cudaMemcpyHostToDevice, f->sU));
+  DVT_CUDA_OK(cudaMemsetAsync(f->idx[slot] + n_idx, 0, (size_t)f->bsz * 4, f->sU));  // rows of the (unused) encode of step num_iters
+  DVT_CUDA_OK(cudaEventRecord(f->ev_upload[slot], f->sU));
+  // ---- schedule tables (dvt/utils/misc.py:306-322), cached: they depend on the hyper-parameters only ----
+  const double key[6] = {(double)num_iters, (double)warmup_iters, lr, min_lr, (double)freeze_step, 1.0};
+  if (memcmp(key, f->sched_key, sizeof(key)) != 0) {
+    std::vector<AdamScalars> a(num_iters + 1), b(num_iters + 1);
+    for (int s = 0; s <= num_iters; ++s) {
+      double lrs;
+      if (s < warmup_iters) lrs = lr * s / warmup_iters;
+      else lrs = min_lr + (lr - min_lr) * 0.5 * (1.0 + cos(M_PI * (s - warmup_iters) / (double)(num_iters - warmup_iters)));
+      const int t = s + 1;
+      a[s].step_size = (float)(lrs / (1.0 - pow(0.9, t)));
+      a[s].inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(0.99, t)));
+      const int tr = s - freeze_step;  // residual MLP: first update at s = freeze_step + 1 has t = 1
+      if (tr >= 1) {
+        b[s].step_size = (float)(lrs / (1.0 - pow(0.9, tr)));
+        b[s].inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(0.99, tr)));
+      } else {
+        b[s].step_size = 0.f; b[s].inv_bc2_sqrt = 1.f;
+      }
+    }
+    DVT_CUDA_OK(cudaStreamSynchronize(f->stream));  // a running fit still reads the old tables
+    DVT_CUDA_OK(cudaMemcpy(f->sc_main, a.data(), a.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
+    DVT_CUDA_OK(cudaMemcpy(f->sc_res, b.data(), b.size() * sizeof(AdamScalars), cudaMemcpyHostToDevice));
+    memcpy(f->sched_key, key, sizeof(key));
+  }
+  // ---- device state, in stream order behind the previous fit and the caller's pending work ----
+  int rc = fit_after_caller(f, caller);
+  if (rc) return rc;
+  cudaStream_t st = f->stream;
+  DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev_upload[slot], 0));
+  fit_set_inputs_kernel<<<1, 1, 0, st>>>(f->inputs_dev, bank, coords, f->idx[slot], f->step_base);
+  fit_check_inputs_kernel<<<256, 256, 0, st>>>(coords, bank_rows * 2, f->idx[slot], n_idx, (int)bank_rows, f->flags_dev);
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch(2);
+  DVT_CUDA_OK(cudaMemsetAsync(f->losses, 0, (size_t)num_iters * 5 * 4, st));
   if (f->cur_host & 1)  // the schedule restarts at step 0, whose state lives in buffer 0
-    DVT_CUDA_OK(cudaMemcpy(f->tb.p[0], f->tb.p[1], f->n_table * 4, cudaMemcpyDeviceToDevice));
+    DVT_CUDA_OK(cudaMemcpyAsync(f->tb.p[0], f->tb.p[1], f->n_table * 4, cudaMemcpyDeviceToDevice, st));
   f->cur_host = 0;
-  DVT_CUDA_OK(cudaMemset(f->tb.m[0], 0, f->n_table * 4)); DVT_CUDA_OK(cudaMemset(f->tb.v[0], 0, f->n_table * 4));
+  DVT_CUDA_OK(cudaMemsetAsync(f->tb.m[0], 0, f->n_table * 4, st));
+  DVT_CUDA_OK(cudaMemsetAsync(f->tb.v[0], 0, f->n_table * 4, st));
   for (int q = 0; q < 3; ++q) {
-    DVT_CUDA_OK(cudaMemset(f->tb.g[q], 0, f->n_table * 4));
-    DVT_CUDA_OK(cudaMemset(f->tb.stamp[q], 0, f->n_table / FIT_F * 4));
+    DVT_CUDA_OK(cudaMemsetAsync(f->tb.g[q], 0, f->n_table * 4, st));
+    DVT_CUDA_OK(cudaMemsetAsync(f->tb.stamp[q], 0, f->n_table / FIT_F * 4, st));
   }
   f->enc_ready = false;
   f->epoch_steps = 0;
-  DVT_CUDA_OK(cudaMemset(f->sm, 0, (size_t)f->n_small * 4)); DVT_CUDA_OK(cudaMemset(f->sv, 0, (size_t)f->n_small * 4));
-  DVT_CUDA_OK(cudaMemset(f->sg, 0, (size_t)f->n_small * 4));
-  fit_split_kernel<<<256, 256>>>(f->sp, f->wsplit, (size_t)f->n_small);
+  DVT_CUDA_OK(cudaMemsetAsync(f->sm, 0, (size_t)f->n_small * 4, st));
+  DVT_CUDA_OK(cudaMemsetAsync(f->sv, 0, (size_t)f->n_small * 4, st));
+  DVT_CUDA_OK(cudaMemsetAsync(f->sg, 0, (size_t)f->n_small * 4, st));
+  fit_split_kernel<<<256, 256, 0, st>>>(f->sp, f->wsplit, (size_t)f->n_small);
   DVT_CUDA_OK(cudaGetLastError());
-  DVT_CUDA_OK(cudaDeviceSynchronize());
+  count_launch();
+  if (validate) return fit_check(f);
   return DVT_OK;
 }
 
@@ -1014,7 +1192,7 @@ static int fit_launch_sweep(Fit* f, int step_off, bool phase2, cudaStream_t st) 
 // on the fly.
 static int fit_enqueue_encode(Fit* f, int step_off, int npeek, cudaStream_t st) {
   const int n = f->bsz;
-  const StepRows sr{f->idx, f->step_base, step_off, f->inputs_dev};
+  const StepRows sr{nullptr, f->step_base, step_off, f->inputs_dev};
   const int tb = 256, blocks = (n * f->grid.n_levels * 4 + tb - 1) / tb;
   DVT_CUDA_OK(launch_k(f->pdl, fit_encode_kernel, dim3(blocks), dim3(tb), 0, st, f->grid, f->tb, nullptr, f->coords, sr, n,
                        f->enc, f->ld_enc, (size_t)n * f->ld_enc, f->sc_main, f->wd, npeek));
@@ -1037,7 +1215,7 @@ static int fit_enqueue_encode(Fit* f, int step_off, int npeek, cudaStream_t st) 
 // Sequential schedule (f->pipe[phase] == false): encode(t) at the head of the step, sweep(t) on the main stream at its tail.
 static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, int impl) {
   const int n = f->bsz, C = f->C, H1 = C / 2, Hr = C / 4, Lf = f->Lf;
-  const StepRows sr{f->idx, f->step_base, step_off, f->inputs_dev};
+  const StepRows sr{nullptr, f->step_base, step_off, f->inputs_dev};
   const int tb = 256;
   const int enc_blocks = (n * f->grid.n_levels + tb - 1) / tb;
   float* sp = f->sp; float* sg = f->sg;
@@ -1179,14 +1357,11 @@ static int fit_capture(Fit* f, bool phase2, int steps, cudaStream_t st, int impl
 // Runs steps [cur, cur + count) of the schedule installed by fit_begin.  use_graphs: 0 = plain launches,
 // k > 0 = CUDA graphs of k steps each (remainders and the phase boundary fall back to plain launches).
 int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
-  DVT_REQUIRE(f->bank && f->idx, "fit_run: call fit_begin first");
-  int cur = 0;
-  DVT_CUDA_OK(cudaMemcpyAsync(&cur, f->step_base, 4, cudaMemcpyDeviceToHost, caller));
-  DVT_CUDA_OK(cudaStreamSynchronize(caller));
+  DVT_REQUIRE(f->bank && f->idx[0], "fit_run: call fit_begin first");
+  int cur = f->cur_step;  // host mirror of the device step counter: no read-back, no host synchronisation
   // order the engine's stream after everything already enqueued on the caller's stream (the bank is produced there)
   cudaStream_t st = f->stream;
-  DVT_CUDA_OK(cudaEventRecord(f->ev_in, caller));
-  DVT_CUDA_OK(cudaStreamWaitEvent(st, f->ev_in, 0));
+  FIT_RC(fit_after_caller(f, caller));
   DVT_REQUIRE(count >= 0 && cur + count <= f->num_iters, "fit_run: %d steps from %d exceed the schedule of %d", count, cur,
               f->num_iters);
   const int end = cur + count;
@@ -1224,9 +1399,10 @@ int fit_run(Fit* f, int count, int use_graphs, cudaStream_t caller, int impl) {
   }
   FIT_RC(fit_sync_sweep(f, st));
   f->cur_host = end;
-  DVT_CUDA_OK(cudaEventRecord(f->ev_out, st));
-  DVT_CUDA_OK(cudaStreamWaitEvent(caller, f->ev_out, 0));
-  return DVT_OK;
+  f->cur_step = end;
+  DVT_CUDA_OK(cudaEventRecord(f->ev_run_done[f->idx_slot], st));
+  f->run_done_valid[f->idx_slot] = true;
+  return fit_before_caller(f, caller);
 }
 
 // One dense table sweep (the Adam step of the CURRENT device step counter, state buffer ping-pong not advanced) on `st`:
@@ -1246,8 +1422,17 @@ int fit_sweep_once(Fit* f, int ctas, cudaStream_t st) {
 
 int fit_losses(Fit* f, float* dst_host, int num_iters) {
   DVT_REQUIRE(num_iters == f->num_iters, "fit_losses: schedule has %d steps", f->num_iters);
-  DVT_CUDA_OK(cudaDeviceSynchronize());
+  DVT_CUDA_OK(cudaStreamSynchronize(f->stream));
   DVT_CUDA_OK(cudaMemcpy(dst_host, f->losses, (size_t)num_iters * 5 * 4, cudaMemcpyDeviceToHost));
+  return DVT_OK;
+}
+
+// Same table, copied asynchronously on `caller` (dst should be pinned host memory or device memory); the next fit_begin
+// is ordered after the copy.
+int fit_losses_async(Fit* f, float* dst, int num_iters, cudaStream_t caller) {
+  DVT_REQUIRE(num_iters == f->num_iters, "fit_losses: schedule has %d steps", f->num_iters);
+  FIT_RC(fit_before_caller(f, caller));
+  DVT_CUDA_OK(cudaMemcpyAsync(dst, f->losses, (size_t)num_iters * 5 * 4, cudaMemcpyDefault, caller));
   return DVT_OK;
 }
 
@@ -1268,6 +1453,7 @@ static int fit_query_reserve(Fit* f, int n) {
 int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, int impl) {
   DVT_REQUIRE(coords && out && n > 0, "fit_query: bad arguments");
   FIT_RC(fit_query_reserve(f, n));
+  FIT_RC(fit_before_caller(f, st));
   const int C = f->C, H1 = C / 2;
   const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};
@@ -1286,6 +1472,7 @@ int fit_query(Fit* f, const float* coords, int n, float* out, cudaStream_t st, i
 int fit_residual(Fit* f, const float* raw, int n, float* out, cudaStream_t st, int impl) {
   DVT_REQUIRE(raw && out && n > 0, "fit_residual: bad arguments");
   FIT_RC(fit_query_reserve(f, n));
+  FIT_RC(fit_before_caller(f, st));
   const int C = f->C, Hr = C / 4;
   const size_t cap = (size_t)f->q_cap, wp = (size_t)f->n_small;
   const StepRows sr{nullptr, f->step_base, 0};

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_size_t, c_uint, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdvt_b200.so")
@@ -44,10 +44,13 @@ SIGNATURES = {
     "dvt_fit_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
     "dvt_fit_destroy": (None, [c_void_p]),
-    "dvt_fit_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    "dvt_fit_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),
+    "dvt_fit_init_params": (c_int, [c_void_p, ctypes.c_ulonglong, c_void_p]),
+    "dvt_fit_check": (c_int, [c_void_p]),
+    "dvt_fit_losses_async": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "dvt_fit_get_param": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
-    "dvt_fit_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_float, c_float, c_int, c_float,
-                              c_float, c_float]),
+    "dvt_fit_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_double, c_double, c_int, c_int,
+                              c_double, c_double, c_int, c_void_p]),
     "dvt_fit_run": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dvt_fit_losses": (c_int, [c_void_p, c_void_p, c_int]),
     "dvt_fit_query": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

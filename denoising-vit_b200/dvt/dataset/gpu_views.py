@@ -18,14 +18,19 @@ from .. import ops
 
 
 def sample_view_params(img_chw: torch.Tensor, num_views: int, scale=(0.1, 0.5), ratio=(3.0 / 4.0, 4.0 / 3.0),
-                       horizontal_flip: bool = True) -> Tuple[np.ndarray, np.ndarray]:
-    """boxes int32 [V, 4] = (top, left, height, width), flips int32 [V] (transform.py:48 and :69, per view)."""
+                       horizontal_flip: bool = True, flip_rng=None) -> Tuple[np.ndarray, np.ndarray]:
+    """boxes int32 [V, 4] = (top, left, height, width), flips int32 [V] (transform.py:48 and :69, per view).
+    flip_rng: where the flip decisions are drawn (default: the global numpy RNG, like a single-process run of the
+    reference transform).  The reference's stage-1 driver runs the transform in DataLoader workers, each with its own
+    re-seeded numpy RNG, so its MAIN process's RNG is consumed by the sampling stream only; a driver that wants that
+    stream to stay the reference's passes a private `np.random.RandomState` here."""
+    rng = np.random if flip_rng is None else flip_rng
     probe = torch.empty((3, int(img_chw.shape[-2]), int(img_chw.shape[-1])), device="meta")  # get_params reads the size only
     boxes = np.empty((num_views, 4), dtype=np.int32)
     flips = np.empty((num_views,), dtype=np.int32)
     for v in range(num_views):
         boxes[v] = torchvision.transforms.RandomResizedCrop.get_params(probe, list(scale), list(ratio))
-        flips[v] = int(horizontal_flip and np.random.random() < 0.5)
+        flips[v] = int(horizontal_flip and rng.random_sample() < 0.5)
     return boxes, flips
 
 
@@ -36,13 +41,14 @@ class GpuViewGenerator:
 
     def __init__(self, size, num_views: int = 768, scale=(0.1, 0.5), ratio=(3.0 / 4.0, 4.0 / 3.0), patch_size: int = 14,
                  stride: int = 14, horizontal_flip: bool = True, dtype: torch.dtype = torch.float32,
-                 append_full_image: bool = True):
+                 append_full_image: bool = True, flip_rng=None):
         self.size = (int(size[0]), int(size[1]))
         self.num_views, self.scale, self.ratio = num_views, tuple(scale), tuple(ratio)
         self.horizontal_flip, self.dtype, self.append_full_image = horizontal_flip, dtype, append_full_image
         self.h_patches = (self.size[0] - patch_size) // stride + 1
         self.w_patches = (self.size[1] - patch_size) // stride + 1
         self._full_grid = None
+        self.flip_rng = flip_rng
 
     def __call__(self, image: torch.Tensor, views_out: Optional[torch.Tensor] = None,
                  coords_out: Optional[torch.Tensor] = None):
@@ -57,7 +63,7 @@ class GpuViewGenerator:
             views_out = torch.empty((V + extra, 3, OH, OW), device=image.device, dtype=self.dtype)
         if coords_out is None:
             coords_out = torch.empty((V + extra, self.h_patches, self.w_patches, 2), device=image.device, dtype=torch.float32)
-        boxes, flips = sample_view_params(image, V, self.scale, self.ratio, self.horizontal_flip)
+        boxes, flips = sample_view_params(image, V, self.scale, self.ratio, self.horizontal_flip, self.flip_rng)
         ops.view_crops(image, boxes, flips, self.size, self.h_patches, self.w_patches, views_out[:V], coords_out[:V])
         if extra:
             views_out[V].copy_(image)

@@ -56,7 +56,13 @@ class FitEngine:
     # ---- parameters ------------------------------------------------------------------------------------
     def set_param(self, name: str, t: torch.Tensor):
         t = t.detach().to(dtype=torch.float32).contiguous()
-        check(lib().dvt_fit_set_param(self._h, name.encode(), ptr(t), t.numel()), f"dvt_fit_set_param({name})")
+        check(lib().dvt_fit_set_param(self._h, name.encode(), ptr(t), t.numel(), cur_stream()),
+              f"dvt_fit_set_param({name})")
+
+    def init_params(self, seed: int):
+        """Fresh parameters for the next fit, drawn on the GPU (what constructing new SingleImageDenoiser /
+        NeuralFeatureField modules per image does in the reference, main_img_denoising.py:39-47); no host round trip."""
+        check(lib().dvt_fit_init_params(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, cur_stream()), "dvt_fit_init_params")
 
     def get_param(self, name: str, like: torch.Tensor) -> torch.Tensor:
         out = torch.empty(like.shape, device="cuda", dtype=torch.float32)
@@ -80,8 +86,11 @@ class FitEngine:
 
     # ---- optimisation ----------------------------------------------------------------------------------
     def begin(self, bank_feats: torch.Tensor, bank_coords: torch.Tensor, idx_stream: np.ndarray, *, lr: float,
-              min_lr: float, warmup_iters: int, freeze_after: float, weight_decay: float, loss_scale: float = 1024.0):
-        """bank_feats [rows, C] f32 cuda, bank_coords [rows, 2] f32 cuda, idx_stream int [num_iters, bsz]."""
+              min_lr: float, warmup_iters: int, freeze_after: float, weight_decay: float, loss_scale: float = 1024.0,
+              validate: bool = True):
+        """bank_feats [rows, C] f32 cuda, bank_coords [rows, 2] f32 cuda, idx_stream int [num_iters, bsz].
+        validate=True reports out-of-range coordinates / rows here (blocks until the device has checked them, like the
+        reference's assert); validate=False only enqueues -- call `check()` at the next natural synchronisation point."""
         if not (bank_feats.is_cuda and bank_coords.is_cuda):
             raise _lib.DvtError("the fit engine needs the feature bank on the GPU (no CPU fallback)")
         assert bank_feats.dtype == torch.float32 and bank_feats.is_contiguous() and bank_feats.shape[1] == self.C
@@ -90,9 +99,16 @@ class FitEngine:
         assert idx.ndim == 2 and idx.shape[1] == self.bsz
         self.num_iters = idx.shape[0]
         self._keep = (bank_feats, bank_coords)  # borrowed by the engine
+        # int(args.freeze_shared_artifacts_after * args.num_iters), in double like the reference (main_img_denoising.py:70)
+        freeze_step = int(freeze_after * self.num_iters)
         check(lib().dvt_fit_begin(self._h, ptr(bank_feats), ptr(bank_coords), bank_feats.shape[0],
-                                  idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), self.num_iters, lr, min_lr,
-                                  warmup_iters, freeze_after, weight_decay, loss_scale), "dvt_fit_begin")
+                                  idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), self.num_iters, float(lr),
+                                  float(min_lr), int(warmup_iters), freeze_step, float(weight_decay), float(loss_scale),
+                                  int(validate), cur_stream()), "dvt_fit_begin")
+
+    def check(self):
+        """Raises if a fit begun with validate=False saw coordinates outside [0, 1] or rows outside the bank.  Blocks."""
+        check(lib().dvt_fit_check(self._h), "dvt_fit_check")
 
     def run(self, count: Optional[int] = None, graph_steps: int = 10):
         check(lib().dvt_fit_run(self._h, self.num_iters if count is None else count, graph_steps, cur_stream()),
@@ -102,6 +118,15 @@ class FitEngine:
         out = np.zeros((self.num_iters, 5), np.float32)
         check(lib().dvt_fit_losses(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), self.num_iters),
               "dvt_fit_losses")
+        return out
+
+    def losses_async(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Loss table copied asynchronously on the current stream into `out` (pinned host or device, [num_iters, 5] f32)."""
+        if out is None:
+            out = torch.empty((self.num_iters, 5), dtype=torch.float32).pin_memory()
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == self.num_iters * 5
+        check(lib().dvt_fit_losses_async(self._h, c_void_p(out.data_ptr()), self.num_iters, cur_stream()),
+              "dvt_fit_losses_async")
         return out
 
     def query(self, coords: torch.Tensor, assume_valid: bool = False) -> torch.Tensor:

@@ -327,16 +327,28 @@ class PretrainedViTWrapper(nn.Module):
         patch = int(kwargs.pop("patch_size", self.patch_size))
         if "img_size" in kwargs:
             a["img"] = int(kwargs.pop("img_size"))
+        # The reference builds the backbone with timm `pretrained=True` and fails hard when the checkpoint cannot be had
+        # (vit_wrapper.py:108-112).  Same here: weights come from $DVT_WEIGHTS_DIR/<identifier>.pth; a randomly
+        # initialised backbone is an explicit opt-in (tests, bench: `allow_random_init=True` or DVT_ALLOW_RANDOM_INIT=1),
+        # never a silent fallback -- stage 1 would otherwise write feature files of a random network that its own resume
+        # rule then treats as done.
+        allow_random = bool(kwargs.pop("allow_random_init", False)) or os.environ.get("DVT_ALLOW_RANDOM_INIT", "") == "1"
         model = B200VisionTransformer(model_identifier, patch, a)
         wdir = os.environ.get("DVT_WEIGHTS_DIR", "")
         path = os.path.join(wdir, model_identifier + ".pth") if wdir else ""
+        self.pretrained_loaded = False
         if path and os.path.isfile(path):
             sd = torch.load(path, map_location="cpu")
             sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in sd.items()}
             model.load_state_dict(sd, strict=True)
+            self.pretrained_loaded = True
+        elif allow_random:
+            logger.warning("no local weights for %s: random initialisation (explicitly allowed)", model_identifier)
         else:
-            logger.warning("no local weights for %s (set DVT_WEIGHTS_DIR): using random initialisation",
-                           model_identifier)
+            raise FileNotFoundError(
+                f"pretrained weights for {model_identifier} not found ({path or 'DVT_WEIGHTS_DIR is not set'}); put "
+                f"<DVT_WEIGHTS_DIR>/{model_identifier}.pth in place, or pass allow_random_init=True / set "
+                "DVT_ALLOW_RANDOM_INIT=1 to run with a randomly initialised backbone")
         size = a["img"]
         transformation = transforms.Compose([
             transforms.Resize(size, interpolation=transforms.InterpolationMode.BICUBIC),

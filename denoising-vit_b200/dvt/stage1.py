@@ -28,10 +28,11 @@ class Stage1Config:
     pixel_bsz: int = 2048
     loss_scale: float = 1024.0      # torch.amp.GradScaler("cuda", 2**10), never unscaled (main_img_denoising.py:55,88)
     graph_steps: int = 20
+    log_losses: bool = False        # keep the per-step loss table of every image (out["losses"], pinned host memory)
 
 
 class Stage1Pipeline:
-    def __init__(self, vit: DVT.PretrainedViTWrapper, layer_index: int, input_size, cfg: Stage1Config):
+    def __init__(self, vit: DVT.PretrainedViTWrapper, layer_index: int, input_size, cfg: Stage1Config, seed: int = 0):
         self.vit, self.layer_index, self.cfg = vit, layer_index, cfg
         H, W = input_size
         P, S = vit.patch_size, vit.stride
@@ -42,7 +43,8 @@ class Stage1Pipeline:
         # device-side copies (the reference also builds its modules on the GPU, main_img_denoising.py:39-47)
         self.field = DVT.NeuralFeatureField(feat_dim=self.C, n_levels=cfg.n_levels).cuda()
         self.engine = FitEngine(self.C, self.h, self.w, cfg.pixel_bsz, self.field.meta)
-        self._gen = torch.Generator(device="cuda")
+        self.base_seed = int(seed)               # parameter initialisation of image k uses (base_seed, k)
+        self._image_counter = 0
         # coordinates of the final query (main_img_denoising.py:121-130), uploaded once: a pageable host-to-device copy
         # after the fit would block the host until the fit has finished and serialise run_images
         self._full_coords = make_patch_coordinates(self.h, self.w, 0, 1).to("cuda")
@@ -98,22 +100,18 @@ class Stage1Pipeline:
 
     # ---- HP-2 ----------------------------------------------------------------------------------------------
     def denoise(self, bank: torch.Tensor, coords: torch.Tensor, idx_stream: np.ndarray,
-                init: Optional[Dict[str, torch.Tensor]] = None, seed: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                init: Optional[Dict[str, torch.Tensor]] = None, seed: Optional[int] = None,
+                validate: bool = True) -> Dict[str, torch.Tensor]:
         """bank [V, h, w, C] f32 cuda, coords [V, h, w, 2] in [0,1]; the last view is the un-augmented image.
-        Returns denoised_feats [1, h, w, C] (= neural_field(coords[-1]), what the reference saves) and raw [h, w, C]."""
+        Returns denoised_feats [1, h, w, C] (= neural_field(coords[-1]), what the reference saves) and raw [h, w, C].
+        Every image starts from fresh parameters, like the reference (new SingleImageDenoiser + NeuralFeatureField per
+        image, main_img_denoising.py:39-47); they are drawn on the device.  Nothing here waits for the GPU when
+        validate=False (run_images), so the next image can be enqueued while this fit is running."""
         cfg = self.cfg
-        # fresh modules per image, like the reference (new SingleImageDenoiser + NeuralFeatureField for every image)
-        with torch.device("cuda"):
-            den = DVT.SingleImageDenoiser(self.h, self.w, self.C, layer_index=self.layer_index)
-        if seed is not None:
-            self._gen.manual_seed(seed)
-        with torch.no_grad():
-            p = self.field.neural_field.params
-            p.copy_((torch.rand(p.shape, device="cuda", generator=self._gen) * 2 - 1) * 1e-4)  # tcnn-style U(-1e-4, 1e-4)
-            for m in self.field.mlp:
-                if hasattr(m, "reset_parameters"):
-                    m.reset_parameters()
-        self.engine.load_modules(den, self.field)
+        if seed is None:
+            self._image_counter += 1
+            seed = (self.base_seed << 20) + self._image_counter
+        self.engine.init_params(seed)
         if init is not None:
             for k, v in init.items():
                 self.engine.set_param(k, v)
@@ -121,10 +119,24 @@ class Stage1Pipeline:
         self.engine.begin(bank.reshape(V * self.h * self.w, self.C), coords.reshape(-1, 2).to("cuda", torch.float32).contiguous(),
                           idx_stream, lr=cfg.lr, min_lr=cfg.min_lr, warmup_iters=cfg.warmup_iters,
                           freeze_after=cfg.freeze_shared_artifacts_after, weight_decay=cfg.weight_decay,
-                          loss_scale=cfg.loss_scale)
+                          loss_scale=cfg.loss_scale, validate=validate)
         self.engine.run(graph_steps=cfg.graph_steps)
         denoised = self.engine.query(self._full_coords, assume_valid=True).reshape(1, self.h, self.w, self.C)
-        return {"denoised_feats": denoised, "raw": bank[-1], "denoiser": den}
+        extra = {}
+        if cfg.log_losses:
+            extra["losses"] = self.engine.losses_async()      # valid once `losses_ready` has completed
+            extra["losses_ready"] = torch.cuda.Event()
+            extra["losses_ready"].record()
+        # (a copy: the bank buffer is recycled for the image after next before a pipelined caller reads its result)
+        return {"denoised_feats": denoised, "raw": bank[-1].clone(), **extra}
+
+    def export_modules(self):
+        """The fitted parameters as the reference's module objects (`SingleImageDenoiser`, `NeuralFeatureField`), e.g. for
+        `visualize_offline_denoised_samples`-style inspection.  Blocks; not used by the per-image loop."""
+        with torch.device("cuda"):
+            den = DVT.SingleImageDenoiser(self.h, self.w, self.C, layer_index=self.layer_index)
+        self.engine.store_modules(den, self.field)
+        return den, self.field
 
     # ---- both paths, software-pipelined over images -----------------------------------------------------------
     def run_images(self, n_images: int, views_fn, coords_fn, idx_fn, finalize, events: Optional[list] = None,
@@ -136,6 +148,8 @@ class Stage1Pipeline:
           idx_fn(i)    -> int [num_iters, pixel_bsz] sampled bank rows  finalize(i, out) -> result (may block, e.g. D2H)
         events: optional list receiving ("hp1" | "hp2", start_event, end_event) per image (timing events recorded on the
         stream that runs the path).  overlap=False: strictly one image after the other (for A/B measurements)."""
+        if n_images <= 0:
+            return []
         if self._extract_stream is None:
             self._extract_stream = torch.cuda.Stream(priority=0)   # lowest priority: the fit's short kernels go first
             self._ext_done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -170,16 +184,17 @@ class Stage1Pipeline:
         results = []
         bank = enqueue_extract(0, make_views(0))
         idx = idx_fn(0)
+        pending = None                             # (i, out) of the previous image: finalised one iteration late
         for i in range(n_images):
-            # The views of the NEXT image are produced now, i.e. behind the forwards of image i and BEFORE the fit of image i
-            # is enqueued: the fit's set-up synchronises with the device, so a view-generation kernel never runs beside the
-            # fit (a low-priority kernel of 228 k tiny CTAs beside the latency-bound fit was measured to cost 250 ms).
+            # The views of the NEXT image are produced now, i.e. behind the forwards of image i and in front of the fit of
+            # image i on the device time line (a low-priority kernel of 228 k tiny CTAs beside the latency-bound fit was
+            # measured to cost 250 ms).
             views_next = make_views(i + 1) if i + 1 < n_images else None
             main.wait_event(self._ext_done[i % 2])
             if tev:
                 a = tev()
                 a.record(main)
-            out = self.denoise(bank, coords_fn(i), idx)
+            out = self.denoise(bank, coords_fn(i), idx, validate=False)   # enqueue only: the host does not wait for the fit
             if tev:
                 b = tev()
                 b.record(main)
@@ -188,6 +203,13 @@ class Stage1Pipeline:
             if i + 1 < n_images:                   # enqueued while the GPU runs the fit of image i
                 bank = enqueue_extract(i + 1, views_next)
                 idx = idx_fn(i + 1)
-            results.append(finalize(i, out))
+            # finalize() may block (device-to-host reads): the results of image i-1 are collected only now, after image i
+            # has been enqueued completely, so the GPU always has the next fit queued behind the running one
+            if pending is not None:
+                results.append(finalize(*pending))
+            pending = (i, out)
+        if pending is not None:
+            results.append(finalize(*pending))
         main.wait_stream(sx)
+        self.engine.check()   # input validation of all fits of this call (blocks: the results are about to be read anyway)
         return results

@@ -154,21 +154,36 @@ int dvt_fit_create(dvt_fit_t** out, int feat_dim, int gh, int gw, int bsz, int n
                    const uint32_t* res_host, const uint32_t* size_host, const uint32_t* offset_host,
                    const uint32_t* hashed_host);
 void dvt_fit_destroy(dvt_fit_t* h);
+/* Stream discipline: calls that change engine state (init_params, set_param, begin, run) are ordered after the work
+ * already enqueued on `stream` and run on the engine's own streams; calls that read state (query, residual,
+ * losses_async) are ordered after the engine on `stream`.  None of them waits for the device on the host unless stated,
+ * so a driver can enqueue the next image while the current fit is running. */
 /* Parameters by name, fp32, host or device: "G" (shared_artifacts [1,C,gh,gw]), "res.{0,2,4}.{weight,bias}"
  * (residual_predictor), "table" (tcnn params, [entries*8]), "mlp.{0,2}.{weight,bias}" (NeuralFeatureField.mlp). */
-int dvt_fit_set_param(dvt_fit_t* h, const char* name, const float* src, size_t numel);
-int dvt_fit_get_param(dvt_fit_t* h, const char* name, float* dst, size_t numel);
+int dvt_fit_set_param(dvt_fit_t* h, const char* name, const float* src, size_t numel, void* stream);
+int dvt_fit_get_param(dvt_fit_t* h, const char* name, float* dst, size_t numel);   /* blocks */
+/* Fresh parameters for the next fit, drawn on the device from a counter-based generator: what constructing new
+ * SingleImageDenoiser / NeuralFeatureField modules does per image in the reference (main_img_denoising.py:39-47):
+ * table U(-1e-4, 1e-4) (tcnn default), nn.Linear default init for the MLPs, G = randn * 0.02 (offline_denoiser.py:33-36). */
+int dvt_fit_init_params(dvt_fit_t* h, unsigned long long seed, void* stream);
 /* Starts a fit: zeroes Adam state, installs the bank (device, borrowed: feats f32 [rows, C], coords f32 [rows, 2],
  * rows = views*gh*gw, row r belongs to noise-map cell r % (gh*gw)), the sampling stream idx_host int32
- * [num_iters, bsz] (np.random.randint replay) and the schedule (adjust_learning_rate, dvt/utils/misc.py:306-322;
- * freeze step = int(freeze_after * num_iters)). */
+ * [num_iters, bsz] (np.random.randint replay; copied before the call returns) and the schedule
+ * (adjust_learning_rate, dvt/utils/misc.py:306-322).  freeze_step = int(args.freeze_shared_artifacts_after *
+ * args.num_iters), computed by the caller in double like the reference (main_img_denoising.py:70).  validate != 0: the
+ * range checks (coordinates in [0, 1] -- the assert of neural_feature_field.py:47 -- and sampled rows inside the bank)
+ * are read back and reported by this call (blocks); validate == 0: they are recorded on the device for dvt_fit_check. */
 int dvt_fit_begin(dvt_fit_t* h, const float* bank_feats, const float* bank_coords, size_t bank_rows,
-                  const int32_t* idx_host, int num_iters, float lr, float min_lr, int warmup_iters, float freeze_after,
-                  float weight_decay, float loss_scale);
+                  const int32_t* idx_host, int num_iters, double lr, double min_lr, int warmup_iters, int freeze_step,
+                  double weight_decay, double loss_scale, int validate, void* stream);
+/* Reports (and clears) the input-validation result of the fits begun since the last check.  Blocks. */
+int dvt_fit_check(dvt_fit_t* h);
 /* Runs the next `count` optimisation steps.  graph_steps > 0: CUDA graphs of that many steps. */
 int dvt_fit_run(dvt_fit_t* h, int count, int graph_steps, void* stream);
 /* Per-step losses, HOST f32 [num_iters, 5]: loss, patch_l2, cosine_similarity, residual, residual_sparsity. */
-int dvt_fit_losses(dvt_fit_t* h, float* dst_host, int num_iters);
+int dvt_fit_losses(dvt_fit_t* h, float* dst_host, int num_iters);   /* blocks */
+/* Same table copied asynchronously on `stream` into pinned-host or device memory. */
+int dvt_fit_losses_async(dvt_fit_t* h, float* dst, int num_iters, void* stream);
 /* out [n, C] f32 = neural_field(coords [n, 2])  (denoised_feats of the final query, main_img_denoising.py:121-130). */
 int dvt_fit_query(dvt_fit_t* h, const float* coords, int n, float* out, void* stream);
 /* out [n, C] f32 = residual_predictor(raw [n, C] f32). */

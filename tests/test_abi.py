@@ -53,7 +53,7 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.DvtError):
         ops.gemm_tn(a, a)
     import dvt.models as DVT
-    w = DVT.PretrainedViTWrapper("vit_small_patch14_dinov2.lvd142m", stride=14)
+    w = DVT.PretrainedViTWrapper("vit_small_patch14_dinov2.lvd142m", stride=14, allow_random_init=True)
     with pytest.raises(_lib.DvtError):
         w.get_intermediate_layers(torch.zeros(1, 3, 28, 28), n=[11])
 
@@ -63,3 +63,17 @@ def test_error_reporting_without_gpu():
     L = _lib.lib()
     rc = L.dvt_set_debug_impl(7)
     assert rc == 1 and b"impl must be" in L.dvt_last_error()
+
+
+def test_missing_weights_raise_unless_random_init_is_explicit(monkeypatch):
+    """Advisor finding (round 1): a backbone without pretrained weights must not be a silent fallback -- the reference
+    builds it with timm `pretrained=True` and fails when the checkpoint is unavailable (vit_wrapper.py:108-112)."""
+    import dvt.models as DVT
+    monkeypatch.delenv("DVT_ALLOW_RANDOM_INIT", raising=False)
+    monkeypatch.delenv("DVT_WEIGHTS_DIR", raising=False)
+    with pytest.raises(FileNotFoundError):
+        DVT.PretrainedViTWrapper("vit_small_patch14_dinov2.lvd142m", stride=14)
+    w = DVT.PretrainedViTWrapper("vit_small_patch14_dinov2.lvd142m", stride=14, allow_random_init=True)
+    assert w.pretrained_loaded is False
+    monkeypatch.setenv("DVT_ALLOW_RANDOM_INIT", "1")
+    DVT.PretrainedViTWrapper("vit_small_patch14_dinov2.lvd142m", stride=14)

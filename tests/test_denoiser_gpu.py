@@ -43,7 +43,7 @@ def test_denoiser_behind_the_frozen_vit():
     from oracle import vit as OV
     ident = "vit_small_patch14_dinov2.lvd142m"
     torch.manual_seed(0)
-    vit = DVT.PretrainedViTWrapper(ident, stride=14)
+    vit = DVT.PretrainedViTWrapper(ident, stride=14, allow_random_init=True)
     with torch.no_grad():
         for b in vit.model.blocks:
             b.ls1.gamma.uniform_(0.5, 1.5)

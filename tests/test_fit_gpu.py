@@ -362,3 +362,118 @@ def test_fit_full_size_schedules_agree(monkeypatch):
     assert np.allclose(la, lb, rtol=2e-3, atol=1e-5)
     assert _min_cos(qa, qb) > 0.9999
     assert la[-1, 0] < la[8, 0], "the loss must fall over the run"
+
+
+def test_fit_headline_2000_steps_matches_reference_golden():
+    """THE full-length trajectory at the headline size: C 768, 37 x 37, 16 levels (19.7 M-entry table with
+    the hashed level), 2048 pixels per step, 2000 steps across the phase boundary, default schedule knobs (software-
+    pipelined sweep, CUDA graphs of 20 steps), against the run of the REFERENCE's own SingleImageDenoiser + torch Adam
+    loop stored by tests/golden/make_fit_golden_headline.py.  Tolerances: final denoised_feats cosine >= 0.999 per patch
+    (north_star), every logged loss term within 2 % (+1e-3 absolute)."""
+    from dvt.fit import FitEngine
+    path = os.path.join(GOLD, "fit_headline_2000.npz")
+    assert os.path.isfile(path), "tests/golden/fit_headline_2000.npz missing (tests/golden/make_fit_golden_headline.py)"
+    cfg, z = _golden("headline_2000")
+    feats, coords, init, idx, den, field, _ = _setup(cfg)
+    assert int(idx.sum()) == int(z["idx_checksum"][0])
+    eng = FitEngine(cfg["C"], cfg["h"], cfg["w"], cfg["bsz"], field.meta)
+    eng.fit(den, field, feats.reshape(-1, cfg["C"]).cuda().contiguous(), coords.reshape(-1, 2).cuda().contiguous(), idx,
+            graph_steps=20, lr=cfg["lr"], min_lr=cfg["min_lr"], warmup_iters=cfg["warmup_iters"],
+            freeze_after=cfg["freeze_after"], weight_decay=cfg["weight_decay"], loss_scale=cfg["loss_scale"])
+    denoised = eng.query(coords[-1:].cuda()).cpu()
+    torch.cuda.synchronize()
+    assert _L().device_error() == 0
+    mc = _min_cos(denoised, torch.from_numpy(z["denoised_feats"].astype(np.float32)))
+    assert mc > 0.999, f"denoised_feats min cosine after 2000 steps {mc}"
+    losses = eng.losses()
+    worst = 0.0
+    for row in z["logs"]:
+        s = int(row[0])
+        for j in range(5):
+            ref_v, got_v = row[1 + j], losses[s, j]
+            worst = max(worst, abs(got_v - ref_v) / (abs(ref_v) + 1e-3))
+            assert abs(got_v - ref_v) <= 0.02 * abs(ref_v) + 1e-3, f"step {s} loss[{j}] {got_v} vs {ref_v}"
+    tsum = float(eng.get_param("table", init["table"]).double().sum())
+    assert abs(tsum - float(z["table_sum"][0])) <= 0.02 * float(z["table_sum"][1]) + 1e-3
+    print(f"headline golden: min cosine {mc:.6f}, worst relative loss deviation {worst:.4f}")
+
+
+def test_device_side_init_and_async_begin():
+    """Per-image re-initialisation on the device (dvt_fit_init_params): right distributions, deterministic in the seed,
+    different across seeds; a fit begun without host validation (validate=False) equals one begun with it; bad inputs are
+    reported by begin(validate=True) and, for validate=False, by check()."""
+    import dvt.models as DVT
+    from dvt import _lib
+    from dvt.fit import FitEngine
+    from oracle import fit as OF
+    C, h, w, V, bsz, L, T = 64, 6, 6, 4, 128, 6, 24
+    field = DVT.NeuralFeatureField(feat_dim=C, n_levels=L)
+    den = DVT.SingleImageDenoiser(h, w, C)
+    eng = FitEngine(C, h, w, bsz, field.meta)
+    eng.init_params(123)
+    tab = eng.get_param("table", field.neural_field.params).cpu()
+    assert tab.abs().max().item() <= 1e-4 and abs(tab.mean().item()) < 2e-6
+    assert abs(tab.std().item() - 1e-4 / 3 ** 0.5) < 2e-6                       # U(-1e-4, 1e-4)
+    w1 = eng.get_param("mlp.0.weight", field.mlp[0].weight).cpu()
+    bound = 1.0 / (L * 8) ** 0.5
+    assert w1.abs().max().item() <= bound and abs(w1.std().item() - bound / 3 ** 0.5) < 0.05 * bound
+    G = eng.get_param("G", den.shared_artifacts).cpu()
+    assert G.shape == den.shared_artifacts.shape and abs(G.std().item() - 0.02) < 2e-3 and abs(G.mean().item()) < 2e-3
+    assert 2.5 < G.abs().max().item() / 0.02 < 6.0                               # a normal, not a uniform
+    eng.init_params(123)
+    assert torch.equal(eng.get_param("table", field.neural_field.params).cpu(), tab)
+    eng.init_params(124)
+    assert not torch.equal(eng.get_param("table", field.neural_field.params).cpu(), tab)
+    # validate=False == validate=True
+    feats, coords = OF.synthetic_bank(V, h, w, C, seed=0)
+    bank, bco = feats.reshape(-1, C).cuda().contiguous(), coords.reshape(-1, 2).cuda().contiguous()
+    idx = np.random.RandomState(0).randint(0, V * h * w, (T, bsz))
+    hyper = dict(lr=0.01, min_lr=0.001, warmup_iters=3, freeze_after=0.5, weight_decay=1e-5, loss_scale=1024.0)
+    outs = []
+    for validate in (True, False):
+        eng.init_params(7)
+        eng.begin(bank, bco, idx, validate=validate, **hyper)
+        eng.run(graph_steps=4)
+        outs.append((eng.query(coords[-1:].cuda()).cpu(), eng.losses().copy()))
+        eng.check()
+    assert _min_cos(outs[0][0], outs[1][0]) > 0.99999 and np.allclose(outs[0][1], outs[1][1], rtol=1e-3, atol=1e-6)
+    assert outs[0][1][-1, 0] < outs[0][1][4, 0]
+    # losses_async == losses
+    la = eng.losses_async()
+    torch.cuda.synchronize()
+    assert np.array_equal(la.numpy(), eng.losses())
+    # bad inputs
+    bad_co = bco.clone()
+    bad_co[5, 0] = 1.5
+    with pytest.raises(_lib.DvtError, match=r"coordinates should be in \[0, 1\]"):
+        eng.begin(bank, bad_co, idx, **hyper)
+    bad_idx = idx.copy()
+    bad_idx[3, 3] = V * h * w + 9
+    eng.begin(bank, bco, bad_idx, validate=False, **hyper)
+    eng.run(4, graph_steps=0)                                                    # rows are clamped: no out-of-bounds read
+    with pytest.raises(_lib.DvtError, match="out of range"):
+        eng.check()
+    eng.check()                                                                   # reported once, then cleared
+    assert _lib.device_error() == 0
+
+
+@pytest.mark.parametrize("n_levels,n", [(10, 1369), (6, 37), (16, 5)])
+def test_encode_with_partial_last_warp(n_levels, n):
+    """fit_query's encode with n * n_levels not a multiple of 8 (class-default 10 levels on a 37 x 37 map: the advisor's
+    round-1 finding about full-mask shuffles after an early return) against the fp32 hash-grid op."""
+    import dvt.models as DVT
+    from dvt.fit import FitEngine
+    C = 64
+    field = DVT.NeuralFeatureField(feat_dim=C, n_levels=n_levels).cuda()
+    with torch.no_grad():
+        field.neural_field.params.uniform_(-1, 1, generator=None)
+    den = DVT.SingleImageDenoiser(4, 4, C).cuda()
+    eng = FitEngine(C, 4, 4, 64, field.meta)
+    eng.load_modules(den, field)
+    co = torch.rand(n, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(n))
+    got = eng.query(co)
+    with torch.no_grad():
+        ref = field(co)                       # hash-grid op (fp32 kernel) + torch Linear layers
+    torch.cuda.synchronize()
+    assert (got - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert _L().device_error() == 0

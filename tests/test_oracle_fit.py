@@ -101,3 +101,52 @@ def test_patch_cell_indexing_is_exact():
     cell = rows % (h * w)
     direct = G[0].permute(1, 2, 0).reshape(h * w, C)[cell]
     assert torch.allclose(s, direct, atol=1e-5)
+
+
+@pytest.mark.parametrize("phase2", [False, True])
+def test_module_forward_equals_oracle(phase2):
+    """`dvt.models.SingleImageDenoiser.forward` (the drop-in module, written from its own pieces) against the oracle
+    restatement of offline_denoiser.py:62-171 -- training (2-D) call incl. off-node artifact coordinates (bilinear,
+    align_corners=True, zero padding) and the 4-D visualisation call, both phases, values and gradients."""
+    import dvt.models as DVT
+    C, h, w, n = 32, 5, 6, 64
+    g = torch.Generator().manual_seed(3)
+    meta = HG.grid_meta(4)
+    init = OF.init_params(C, h, w, meta, seed=3)
+    p = {k: v.clone().requires_grad_(True) for k, v in init.items()}
+    den = DVT.SingleImageDenoiser(h, w, C)
+    with torch.no_grad():
+        den.shared_artifacts.copy_(init["G"])
+        for i in (0, 2, 4):
+            den.residual_predictor[i].weight.copy_(init[f"res.{i}.weight"])
+            den.residual_predictor[i].bias.copy_(init[f"res.{i}.bias"])
+    if phase2:
+        den.start_residual_predictor()
+    raw = torch.randn(n, C, generator=g)
+    pc = torch.rand(n, 2, generator=g)
+    gc = torch.rand(n, 2, generator=g) * 2.2 - 1.1          # some samples fall outside [-1, 1]: zero padding
+    gc[: n // 2] = OF.make_patch_coordinates(h, w).reshape(-1, 2)[torch.randint(0, h * w, (n // 2,), generator=g)]
+    field = lambda c: OF.field_forward(p, c, meta)  # noqa: E731
+    got = den(raw, pc, neural_field=field, shared_artifact_coords=gc)
+    want = OF.denoiser_forward(p, raw, pc, meta, gc, phase2)
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.allclose(got[k], want[k], rtol=1e-5, atol=1e-6), k
+    got["loss"].backward()
+    gG = den.shared_artifacts.grad.clone()
+    want["loss"].backward()
+    assert torch.allclose(gG, p["G"].grad, rtol=1e-4, atol=1e-7)
+    if phase2:
+        assert torch.allclose(den.residual_predictor[4].weight.grad, p["res.4.weight"].grad, rtol=1e-4, atol=1e-7)
+    # 4-D call: one map per leading index, G cell by cell
+    raw_hw = torch.randn(1, h, w, C, generator=g)
+    co_hw = OF.make_patch_coordinates(h, w, 0, 1)[None]
+    with torch.no_grad():
+        vis = den(raw_hw, co_hw, neural_field=field, return_visualization=True)
+        q = OF.query({k: v.detach() for k, v in p.items()}, raw_hw, co_hw, meta, phase2)
+    for k in ("denoised_feats", "shared_patterns", "denoised_features") + (("pred_residual",) if phase2 else ()):
+        assert vis[k].shape == (1, h, w, C) and torch.allclose(vis[k], q[k], rtol=1e-5, atol=1e-6), k
+    with pytest.raises(AssertionError):
+        den(raw, pc, neural_field=field)                      # 2-D call without artifact coordinates
+    with pytest.raises(AssertionError):
+        den(raw, pc, neural_field=field, shared_artifact_coords=gc, return_visualization=True)

@@ -13,7 +13,7 @@ def _pipe():
     import dvt.models as DVT
     from dvt.stage1 import Stage1Config, Stage1Pipeline
     torch.manual_seed(0)
-    vit = DVT.PretrainedViTWrapper("vit_small_patch14_dinov2.lvd142m", stride=14)
+    vit = DVT.PretrainedViTWrapper("vit_small_patch14_dinov2.lvd142m", stride=14, allow_random_init=True)
     with torch.no_grad():
         for b in vit.model.blocks:
             b.ls1.gamma.fill_(1.0)
@@ -24,8 +24,7 @@ def _pipe():
 
 
 def _run(pipe, views_list, coords, overlap):
-    torch.manual_seed(7)                 # per-image module re-initialisation (torch's CUDA generator)
-    pipe._gen.manual_seed(11)            # hash-table initialisation
+    pipe._image_counter = 0              # per-image parameter initialisation is a function of (seed, image number)
     n_rows = coords.shape[0] * pipe.h * pipe.w
 
     def idx_fn(i):
@@ -112,3 +111,112 @@ def test_view_crops_against_oracle_at_full_size_and_errors():
         ops.view_crops(img.cuda(), [[500, 0, 40, 40]], [0], (64, 64), 4, 4)
     with pytest.raises(_lib.DvtError):
         gen(img)                                                                # CPU tensor: no fallback
+
+
+# ---- end to end against the oracle (BASELINE.json configs[0]) -------------------------------------------------------
+def test_stage1_config1_end_to_end_matches_oracle():
+    """BASELINE config 1, the reference's own CPU-runnable case: one 224 x 224 image, DINOv2 ViT-S/14 (random init,
+    non-degenerate LayerScale, position embedding resampled 37 -> 16), 8 augmented views + the image, 50-step fit, loss
+    scale 1 -- `Stage1Pipeline` (views -> bank -> fit -> map, all on the GPU) against oracle ViT -> oracle fit on the same
+    views, initial parameters and sampling stream.  Tolerance: cosine >= 0.999 on the bank and on the denoised map."""
+    import dvt.models as DVT
+    from dvt.dataset import GpuViewGenerator
+    from dvt.stage1 import Stage1Config, Stage1Pipeline
+    from oracle import fit as OF
+    from oracle import hashgrid as HG
+    from oracle import vit as OV
+    ident = "vit_small_patch14_dinov2.lvd142m"
+    vcfg = OV.CONFIGS[ident]
+    sd = OV.random_state_dict(vcfg, seed=0)                 # LayerScale gammas resampled U(0.5, 1.5)
+    vit = DVT.PretrainedViTWrapper(ident, stride=14, allow_random_init=True)
+    vit.model.load_state_dict(sd)
+    vit = vit.cuda().eval()
+    V, T, bsz, L = 8, 50, 256, 16
+    cfg = Stage1Config(num_iters=T, warmup_iters=5, n_levels=L, extract_bsz=4, pixel_bsz=bsz, loss_scale=1.0, graph_steps=5)
+    pipe = Stage1Pipeline(vit, layer_index=vcfg.depth - 1, input_size=(224, 224), cfg=cfg)
+    assert (pipe.h, pipe.w, pipe.C) == (16, 16, 384)
+    img = torch.rand(3, 224, 224, generator=torch.Generator().manual_seed(0))
+    mean, std = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1), torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    img = (img - mean) / std
+    torch.manual_seed(1)
+    np.random.seed(1)
+    gen = GpuViewGenerator((224, 224), num_views=V)
+    views, coords = gen(img.cuda())
+    bank = pipe.extract_bank(views)
+    # oracle bank from the SAME views (view generation has its own golden test)
+    ref_bank = OV.forward_intermediates(sd, vcfg, views.cpu(), [vcfg.depth - 1], stride=14)[0].permute(0, 2, 3, 1).contiguous()
+    assert F.cosine_similarity(bank.cpu().reshape(-1, 384), ref_bank.reshape(-1, 384), dim=-1).min().item() > 0.999
+    meta = HG.grid_meta(L)
+    init = OF.init_params(384, 16, 16, meta, seed=3)
+    idx = np.random.RandomState(3).randint(0, (V + 1) * 256, (T, bsz))
+    hyper = dict(lr=cfg.lr, min_lr=cfg.min_lr, weight_decay=cfg.weight_decay, warmup_iters=cfg.warmup_iters,
+                 freeze_after=cfg.freeze_shared_artifacts_after, loss_scale=cfg.loss_scale)
+    ora = OF.fit(ref_bank, coords.cpu(), 16, 16, meta, init, idx, **hyper)
+    out = pipe.denoise(bank, coords, idx, init=init)
+    losses = pipe.engine.losses()
+    torch.cuda.synchronize()
+    from dvt import _lib
+    assert _lib.device_error() == 0
+    got, ref = out["denoised_feats"].cpu(), ora["denoised_feats"]
+    assert got.shape == ref.shape == (1, 16, 16, 384)
+    c = F.cosine_similarity(got.reshape(-1, 384), ref.reshape(-1, 384), dim=-1).min().item()
+    assert c > 0.999, f"end-to-end denoised map min cosine {c}"
+    assert torch.equal(out["raw"], bank[-1])
+    for row in ora["logs"]:
+        s = int(row[0])
+        assert abs(losses[s, 0] - row[1]) <= 0.03 * abs(row[1]) + 1e-3, f"step {s}: loss {losses[s, 0]} vs oracle {row[1]}"
+
+
+def test_stage1_cli_writes_the_store(tmp_path, monkeypatch, capsys):
+    """The drop-in command line itself (main_img_denoising.py) on synthetic JPEGs: two images pipelined, `.npy` store
+    written by the background writer in the reference's layout, the raw map equal to the ViT features of the un-augmented
+    image, and a second invocation skipping both images (resume rule, reference :303-307)."""
+    import os
+    import sys
+    from PIL import Image
+    monkeypatch.setenv("DVT_ALLOW_RANDOM_INIT", "1")        # no pretrained checkpoints on the test box
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import main_img_denoising as M
+    from dvt.store import load_pair
+    from dvt.utils import misc
+    data_root = str(tmp_path / "data") + "/"
+    rels = ["set/a.jpg", "set/b.jpg"]
+    rs = np.random.RandomState(0)
+    for rel in rels:
+        os.makedirs(os.path.dirname(os.path.join(data_root, rel)), exist_ok=True)
+        Image.fromarray(rs.randint(0, 255, (90, 120, 3), dtype=np.uint8)).save(os.path.join(data_root, rel))
+    lst = tmp_path / "list.txt"
+    lst.write_text("".join(f"{r}\n" for r in rels))
+    argv = ["--model", "vit_small_patch14_dinov2.lvd142m", "--input_size", "70", "84", "--stride_size", "14",
+            "--img_path", str(lst), "--data_root", data_root, "--save_root", str(tmp_path / "feats"), "--num_views", "6",
+            "--num_iters", "40", "--warmup_iters", "4", "--n_levels", "6", "--extract_bsz", "4", "--pixel_bsz", "64",
+            "--output_dir", str(tmp_path / "work"), "--seed", "3", "--collate_out", str(tmp_path / "maps.pt")]
+    args = M.get_args(argv)
+    M.main(args)
+    text = capsys.readouterr().out
+    assert text.count("Step 39/39: Loss = ") == 2 and "Saving denoised features to" in text
+    for rel in rels:
+        raw_p, den_p = misc.feature_paths(args, os.path.join(data_root, rel))
+        assert os.path.isfile(raw_p) and os.path.isfile(den_p)
+        raw, den = load_pair(den_p)
+        assert raw.shape == (5, 6, 384) and den.shape == (5, 6, 384) and raw.dtype == np.float32
+        assert np.isfinite(raw).all() and np.isfinite(den).all() and np.abs(den).max() > 0
+        assert np.load(den_p).shape == (1, 5, 6, 384)
+    packed = torch.load(str(tmp_path / "maps.pt"))
+    assert packed["denoised_feats"].shape == (2, 5, 6, 384) and len(packed["files"]) == 2
+    assert np.array_equal(packed["denoised_feats"][1].numpy(), load_pair(misc.feature_paths(args, os.path.join(data_root, rels[1]))[1])[1])
+    # the raw map is the ViT feature map of the un-augmented image
+    import dvt.models as DVT
+    from dvt.dataset import load_image
+    misc.fix_random_seeds(3)     # the CLI's randomly initialised backbone is seeded by fix_random_seeds(args.seed)
+    vit = DVT.PretrainedViTWrapper(args.model, stride=14).cuda().eval()
+    norm = vit.transformation.transforms[-1]
+    x = load_image(os.path.join(data_root, rels[0]), (70, 84), norm.mean, norm.std)[None].cuda()
+    feat = vit.get_intermediate_layers(x, n=[11], reshape=True)[-1].permute(0, 2, 3, 1)[0].cpu().numpy()
+    raw0, _ = load_pair(misc.feature_paths(args, os.path.join(data_root, rels[0]))[1])
+    assert np.abs(raw0 - feat).max() < 1e-4 * max(1.0, np.abs(feat).max())
+    # second run: everything is skipped
+    M.main(M.get_args(argv))
+    text = capsys.readouterr().out
+    assert text.count("Skipping") == 2 and "Step 39/39" not in text

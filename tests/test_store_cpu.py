@@ -36,39 +36,102 @@ def test_lr_schedule_matches_reference():
             assert abs(OF.lr_at(it, s["lr"], s["min_lr"], s["warmup_iters"], s["num_iters"]) - ref) <= 1e-15
 
 
-def test_stage1_driver_writes_the_reference_store(tmp_path):
-    """`denoise_an_image` of the drop-in CLI with a stub pipeline: file locations, dtypes and shapes of the store, and the
-    resume check that makes a second run skip the image."""
-    sys.path.insert(0, ROOT)
-    import main_img_denoising as M
+def test_feature_store_writer_writes_the_reference_store(tmp_path):
+    """`dvt.store.FeatureStoreWriter` (what the drop-in CLI hands every image's maps to): file locations, dtypes and shapes
+    of the store (main_img_denoising.py:131-146), NPY v1, atomic rename, and the resume check that makes a second run skip
+    the image."""
+    from dvt.store import FeatureStoreWriter, load_pair
     from dvt.utils import misc
-    h, w, C, V = 4, 5, 32, 3
-
-    class Engine:
-        def losses(self):
-            return np.zeros((20, 5), np.float32)
-
-    class Pipe:
-        engine = Engine()
-
-        def denoise(self, feats, coords, idx):
-            assert idx.shape == (20, 8) and idx.max() < V * h * w
-            return {"denoised_feats": torch.ones(1, h, w, C), "raw": feats[-1], "denoiser": None}
-
+    h, w, C = 4, 5, 32
     data_root = str(tmp_path / "imgs")
-    args = Namespace(num_iters=20, pixel_bsz=8, lr=0.01, min_lr=0.001, warmup_iters=2, data_root=data_root,
-                     save_root=str(tmp_path / "store"), model="vit_base_patch14_dinov2.lvd142m")
+    args = Namespace(data_root=data_root, save_root=str(tmp_path / "store"), model="vit_base_patch14_dinov2.lvd142m")
     img = os.path.join(data_root, "sub", "x.jpg")
     assert not misc.check_if_file_exists(args, img)
-    feats = torch.arange(V * h * w * C, dtype=torch.float32).reshape(V, h, w, C)
-    np.random.seed(0)
-    M.denoise_an_image(args, Pipe(), feats, torch.zeros(V, h, w, 2), img_pth=img)
+    raw_t = torch.arange(h * w * C, dtype=torch.float32).reshape(h, w, C)
+    den_t = torch.ones(1, h, w, C)
     raw_p, den_p = misc.feature_paths(args, img)
+    wr = FeatureStoreWriter(max_pending=2)
+    for k in range(5):                                   # more submissions than staging slots: back-pressure, buffer reuse
+        wr.submit(raw_p.replace("x.npy", f"x{k}.npy"), den_p.replace("x.npy", f"x{k}.npy"), raw_t + k, den_t * k)
+    wr.submit(raw_p, den_p, raw_t, den_t)
+    wr.close()
+    assert len(wr.written) == 6
     # (the doubled slash is the reference's: data_root without a trailing slash is replaced by a directory with one)
     assert os.path.normpath(raw_p).endswith("store/raw_features/vit_base_patch14_dinov2.lvd142m/sub/x.npy")
     raw, den = np.load(raw_p), np.load(den_p)
-    assert raw.dtype == np.float32 and raw.shape == (h, w, C) and np.array_equal(raw, feats[-1].numpy())
+    assert raw.dtype == np.float32 and raw.shape == (h, w, C) and np.array_equal(raw, raw_t.numpy())
     assert den.dtype == np.float32 and den.shape == (1, h, w, C)
+    assert np.array_equal(np.load(raw_p.replace("x.npy", "x3.npy")), (raw_t + 3).numpy())
     with open(raw_p, "rb") as f:
         assert f.read(8) == bytes([0x93]) + b"NUMPY" + bytes([1, 0])          # NPY format version 1.0
+    assert not [n for n in os.listdir(os.path.dirname(raw_p)) if ".tmp." in n]
     assert misc.check_if_file_exists(args, img)
+    r2, d2 = load_pair(den_p)
+    assert r2.shape == (h, w, C) and d2.shape == (h, w, C)
+    bad = FeatureStoreWriter()
+    bad.submit("/proc/definitely/not/writable/r.npy", "/proc/definitely/not/writable/d.npy", raw_t, den_t)
+    try:
+        bad.close()
+        raise AssertionError("write error was swallowed")
+    except RuntimeError as e:
+        assert "feature store write failed" in str(e)
+
+
+def test_store_reads_back_through_the_reference_dataset(tmp_path):
+    """The store written here, read by the REFERENCE's stage-2 dataset (dvt/dataset/paired_list_dataset.py:27-43,
+    imported unmodified).  Runs in the build container only (needs /root/reference)."""
+    import importlib.util
+    import pytest
+    ref_file = "/root/reference/dvt/dataset/paired_list_dataset.py"
+    if not os.path.isfile(ref_file):
+        pytest.skip("reference checkout not present on this machine")
+    from PIL import Image
+    from dvt.store import FeatureStoreWriter
+    from dvt.utils import misc
+    spec = importlib.util.spec_from_file_location("ref_paired", ref_file)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    h, w, C = 3, 4, 16
+    data_root = str(tmp_path / "data") + "/"
+    model = "vit_small_patch14_dinov2.lvd142m"
+    args = Namespace(data_root=data_root, save_root=str(tmp_path / "feats"), model=model)
+    rels = ["a/one.jpg", "b/two.png"]
+    wr = FeatureStoreWriter()
+    maps = {}
+    for k, rel in enumerate(rels):
+        os.makedirs(os.path.dirname(os.path.join(data_root, rel)), exist_ok=True)
+        Image.fromarray(np.full((8, 8, 3), 40 * k, np.uint8)).save(os.path.join(data_root, rel))
+        g = torch.Generator().manual_seed(k)
+        maps[rel] = (torch.randn(h, w, C, generator=g), torch.randn(1, h, w, C, generator=g))
+        wr.submit(*misc.feature_paths(args, os.path.join(data_root, rel)), *maps[rel])
+    wr.close()
+    lst = tmp_path / "list.txt"
+    lst.write_text("".join(f"{r} 0\n" for r in rels))
+    ds = ref.PairedListDataset(data_root=data_root, data_list=str(lst),
+                               feat_root=f"{args.save_root}/denoised_features/{model}/", transform=lambda im: im.size)
+    assert len(ds) == 2
+    for k, rel in enumerate(rels):
+        item = ds[k]
+        assert item["image"] == (8, 8)
+        assert item["original_feats"].shape == (h, w, C) and item["denoised_feats"].shape == (h, w, C)
+        assert np.array_equal(item["original_feats"], maps[rel][0].numpy())
+        assert np.array_equal(item["denoised_feats"], maps[rel][1][0].numpy())
+
+
+def test_sampling_stream_is_the_references_rng_stream():
+    """`draw_sampling_stream` (one int32 draw for all steps, plus the visualisation draw of every vis_freq-th image) leaves
+    the global numpy RNG exactly where the reference's per-step int64 draws do (main_img_denoising.py:73,102)."""
+    sys.path.insert(0, ROOT)
+    import main_img_denoising as M
+    args = Namespace(num_iters=7, pixel_bsz=16, vis_freq=2, num_views=5, num_vis_samples=3)
+    n_rows = 6 * 37 * 37
+    np.random.seed(11)
+    got = [M.draw_sampling_stream(args, n_rows, i) for i in range(3)]
+    tail = np.random.randint(0, 1 << 30, 4)
+    np.random.seed(11)
+    for i in range(3):
+        ref = np.stack([np.random.randint(0, n_rows, args.pixel_bsz) for _ in range(args.num_iters)])
+        if i % args.vis_freq == 0:
+            np.random.randint(0, args.num_views + 1, args.num_vis_samples)
+        assert got[i].dtype == np.int32 and np.array_equal(got[i], ref)
+    assert np.array_equal(tail, np.random.randint(0, 1 << 30, 4))

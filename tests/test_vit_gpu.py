@@ -94,7 +94,7 @@ def _wrapper_from_sd(name, sd, stride, patch_size=None, img=None):
     kw = {}
     if img is not None:
         kw["img_size"] = img
-    w = DVT.PretrainedViTWrapper(name, stride=stride, **kw)
+    w = DVT.PretrainedViTWrapper(name, stride=stride, allow_random_init=True, **kw)
     w.model.load_state_dict(sd, strict=True)
     return w.cuda().eval()
 
@@ -103,6 +103,7 @@ def _wrapper_from_sd(name, sd, stride, patch_size=None, img=None):
 @pytest.mark.parametrize("fixture,ident", [
     ("vit_hf_dinov2.npz", "vit_small_patch14_dinov2.lvd142m"),
     ("vit_hf_dinov2_reg4.npz", "vit_small_patch14_reg4_dinov2.lvd142m"),
+    ("vit_hf_dinov2_swiglu.npz", "vit_giant_patch14_dinov2.lvd142m"),     # SwiGLUPacked MLP (ViT-g/14 family)
 ])
 def test_vit_matches_hf_golden(impl, fixture, ident):
     """CUDA forward vs transformers.Dinov2Model outputs stored by tests/golden/make_vit_golden.py."""

@@ -31,7 +31,7 @@ def t(fn, reps=2):
 def main():
     dev = "cuda"
     V = 769
-    vit = DVT.PretrainedViTWrapper(bench.MODEL, stride=14)
+    vit = DVT.PretrainedViTWrapper(bench.MODEL, stride=14, allow_random_init=True)
     with torch.no_grad():
         for b in vit.model.blocks:
             b.ls1.gamma.fill_(1.0)
