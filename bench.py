@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-kernel-rooflines", action="store_true",
                     help="skip the stand-alone kernel timings (for ncu launch lists of the timed region)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-library-bar", action="store_true",
+                    help="skip the unfused cuBLAS / SDPA / torch.optim restatement timed on the same GPU (tools/library_bar.py)")
     return ap.parse_args()
 
 
@@ -187,64 +189,97 @@ def usable_cpus() -> int:
     return max(1, n)
 
 
-def cpu_reference_rate(args, views_sample: int = 1, fit_steps: int = 2):
-    from oracle import fit as OF
-    from oracle import hashgrid as HG
-    from oracle import vit as OV
-    cores = min(usable_cpus(), 32)  # measured on the GPU box: 128 threads run these ops ~100x slower than 8-32 do
-    torch.set_num_threads(cores)
-    cfg = OV.CONFIGS[MODEL]
-    sd = OV.random_state_dict(cfg, seed=0)
-    x = torch.randn(1, 3, 518, 518, generator=torch.Generator().manual_seed(0))
-    OV.forward_intermediates(sd, cfg, x, [11])  # warm-up
-    t0 = time.perf_counter()
-    for _ in range(views_sample):
-        OV.forward_intermediates(sd, cfg, x, [11])
-    t_view = (time.perf_counter() - t0) / views_sample
-    # fit steps at the full problem size (C 768, 37x37, 16 levels, 2048 pixels); small synthetic bank of 8 views
-    C, h, w, V, bsz = 768, 37, 37, 8, 2048
-    meta = HG.grid_meta(16)
-    feats, coords = OF.synthetic_bank(V, h, w, C, seed=0)
-    init = OF.init_params(C, h, w, meta, seed=0)
-    T = 2 * fit_steps + 2
-    idx = np.random.RandomState(0).randint(0, V * h * w, (T, bsz))
-    p = {k: init[k].clone().float().requires_grad_(True) for k in OF.PARAM_ORDER}
-    opt = torch.optim.Adam([p[k] for k in OF.PARAM_ORDER], lr=0.01, eps=1e-15, weight_decay=1e-5, betas=(0.9, 0.99))
-    g_all = OF.make_patch_coordinates(h, w).unsqueeze(0).repeat(V, 1, 1, 1).reshape(-1, 2)
-    f2, c2 = feats.reshape(-1, C), coords.reshape(-1, 2)
-    times = {False: [], True: []}
-    for step in range(T):
-        phase2 = step > T // 2
-        if phase2:
-            p["G"].requires_grad = False
+def workload_config(args, world: int) -> dict:
+    """`config` of the JSON line -- identical for the B200 arm and the reference arm (same workload, same sizes)."""
+    return {"workload": "stage1_vitb14_518_768views_2000iters", "views_per_image": args.views + 1,
+            "fit_iters": args.num_iters, "fit_warmup_iters": args.warmup_iters, "pixel_bsz": 2048, "n_levels": 16,
+            "extract_bsz": args.extract_bsz, "images_per_gpu": args.steps,
+            "parallelism": f"image-sharded x{world}, one all-gather of denoised maps",
+            "l2": "inputs larger than L2 (2.48 GB of views, 3.2 GB bank, 0.34 GB Adam state per image)"}
+
+
+class CpuReference:
+    """The reference algorithm on the host cores (oracle port, fp32 PyTorch CPU).  Built once (ViT-B/14 weights, the
+    19.7 M-entry table, a small synthetic bank); every `measure()` times a bounded sample of the per-image work:
+    `views_sample` ViT-B/14 forwards at 518^2 and `fit_steps` full-size optimisation steps per phase (one extra warm-up
+    step per phase is not timed), and extrapolates to 769 views + 2000 steps."""
+
+    def __init__(self, args):
+        from oracle import fit as OF
+        from oracle import hashgrid as HG
+        from oracle import vit as OV
+        self.args, self.OF, self.OV = args, OF, OV
+        self.cores = min(usable_cpus(), 32)  # measured on the GPU box: 128 threads run these ops ~100x slower than 8-32 do
+        torch.set_num_threads(self.cores)
+        self.cfg = OV.CONFIGS[MODEL]
+        self.sd = OV.random_state_dict(self.cfg, seed=0)
+        self.x = torch.randn(1, 3, 518, 518, generator=torch.Generator().manual_seed(0))
+        OV.forward_intermediates(self.sd, self.cfg, self.x, [11])  # warm-up
+        # fit steps at the full problem size (C 768, 37x37, 16 levels, 2048 pixels); small synthetic bank of 8 views
+        C, h, w, V = 768, 37, 37, 8
+        self.meta = HG.grid_meta(16)
+        feats, coords = OF.synthetic_bank(V, h, w, C, seed=0)
+        self.init = OF.init_params(C, h, w, self.meta, seed=0)
+        self.g_all = OF.make_patch_coordinates(h, w).unsqueeze(0).repeat(V, 1, 1, 1).reshape(-1, 2)
+        self.f2, self.c2 = feats.reshape(-1, C), coords.reshape(-1, 2)
+        self.rs = np.random.RandomState(0)
+
+    def measure(self, views_sample: int = 1, fit_steps: int = 2):
+        OF, args = self.OF, self.args
         t0 = time.perf_counter()
-        i = torch.from_numpy(idx[step])
-        out = OF.denoiser_forward(p, f2[i], c2[i], meta, g_all[i], phase2)
-        opt.zero_grad()
-        (out["loss"] * 1024.0).backward()
-        opt.step()
-        dt = time.perf_counter() - t0
-        if step not in (0, T // 2 + 1):  # first step of each phase = warm-up
-            times[phase2].append(dt)
-    assert times[False] and times[True], "cpu_reference_rate: fit_steps must be >= 2 (one timed step per phase)"
-    t_p1, t_p2 = float(np.mean(times[False])), float(np.mean(times[True]))
-    n_p2 = args.num_iters - 1 - int(0.5 * args.num_iters)
-    n_p1 = args.num_iters - n_p2
-    per_image = (args.views + 1) * t_view + n_p1 * t_p1 + n_p2 * t_p2
-    return {"value": 1.0 / per_image, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": (f"{views_sample} ViT-B/14 518^2 forwards ({t_view:.3f} s/view) + {len(times[False])}+{len(times[True])} "
-                       f"full-size fit steps ({t_p1:.3f} / {t_p2:.3f} s/step phase 1/2), extrapolated to "
-                       f"{args.views + 1} views + {args.num_iters} steps"),
-            "s_per_view": t_view, "s_per_step_phase1": t_p1, "s_per_step_phase2": t_p2}
+        for _ in range(views_sample):
+            self.OV.forward_intermediates(self.sd, self.cfg, self.x, [11])
+        t_view = (time.perf_counter() - t0) / views_sample
+        T = 2 * fit_steps + 2
+        idx = self.rs.randint(0, self.f2.shape[0], (T, 2048))
+        p = {k: self.init[k].clone().float().requires_grad_(True) for k in OF.PARAM_ORDER}
+        opt = torch.optim.Adam([p[k] for k in OF.PARAM_ORDER], lr=0.01, eps=1e-15, weight_decay=1e-5, betas=(0.9, 0.99))
+        times = {False: [], True: []}
+        for step in range(T):
+            phase2 = step > T // 2
+            if phase2:
+                p["G"].requires_grad = False
+            t0 = time.perf_counter()
+            i = torch.from_numpy(idx[step])
+            out = OF.denoiser_forward(p, self.f2[i], self.c2[i], self.meta, self.g_all[i], phase2)
+            opt.zero_grad()
+            (out["loss"] * 1024.0).backward()
+            opt.step()
+            dt = time.perf_counter() - t0
+            if step not in (0, T // 2 + 1):  # first step of each phase = warm-up
+                times[phase2].append(dt)
+        assert times[False] and times[True], "CpuReference.measure: fit_steps must be >= 2 (one timed step per phase)"
+        t_p1, t_p2 = float(np.mean(times[False])), float(np.mean(times[True]))
+        n_p2 = args.num_iters - 1 - int(0.5 * args.num_iters)
+        n_p1 = args.num_iters - n_p2
+        per_image = (args.views + 1) * t_view + n_p1 * t_p1 + n_p2 * t_p2
+        return {"value": 1.0 / per_image, "unit": "images/s", "cores": self.cores, "kind": "port",
+                "sample": (f"{views_sample} ViT-B/14 518^2 forwards ({t_view:.3f} s/view) + {len(times[False])}+{len(times[True])} "
+                           f"full-size fit steps ({t_p1:.3f} / {t_p2:.3f} s/step phase 1/2), extrapolated to "
+                           f"{args.views + 1} views + {args.num_iters} steps"),
+                "s_per_view": t_view, "s_per_step_phase1": t_p1, "s_per_step_phase2": t_p2}
+
+
+def cpu_reference_rate(args, views_sample: int = 4, fit_steps: int = 10):
+    """`cpu_baseline` of the B200 line: ~10-30 s of CPU work (4 views, 10 + 10 timed steps)."""
+    return CpuReference(args).measure(views_sample, fit_steps)
 
 
 def run_reference_arm(args, rank):
+    """--impl reference: every "step" is a bounded sample of one image's work on the host cores, sized so that the whole
+    --steps K --warmup W run ends within a few minutes (the full per-image CPU run is ~14 min): the per-step sample shrinks
+    as K grows, never below 2 views + 4 timed steps per phase."""
     if rank != 0:
         return
+    ref = CpuReference(args)
+    n_meas = max(1, args.warmup > 0) + args.steps
+    budget = 150.0 / n_meas                                   # seconds of CPU work per step
+    views_sample = int(min(4, max(2, budget * 0.25 / 0.65)))
+    fit_steps = int(min(10, max(4, budget * 0.75 / 0.8)))
     vals, last = [], None
-    for _ in range(max(1, args.warmup > 0) + args.steps):
+    for _ in range(n_meas):
         t0 = time.perf_counter()
-        last = cpu_reference_rate(args, views_sample=1, fit_steps=2)
+        last = ref.measure(views_sample=views_sample, fit_steps=fit_steps)
         vals.append((last["value"], time.perf_counter() - t0))
     vals = vals[1:] if len(vals) > 1 else vals
     v = float(np.mean([a for a, _ in vals]))
@@ -253,8 +288,9 @@ def run_reference_arm(args, rank):
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "stage1_vitb14_518_768views_2000iters", "note": "reference algorithm (oracle port, "
-                       "PyTorch CPU fp32) on a bounded sample per step, extrapolated to one image"},
+            "config": workload_config(args, args.gpus),
+            "arm_notes": "reference algorithm (oracle port, PyTorch CPU fp32) on a bounded sample per step, extrapolated to "
+                         "one image; rank 0 only",
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -460,16 +496,25 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (ViT) / tf32x3 (fit)",
                 "data": "synthetic",
-                "config": {"workload": "stage1_vitb14_518_768views_2000iters", "views_per_image": V,
-                           "fit_iters": args.num_iters, "fit_warmup_iters": args.warmup_iters, "pixel_bsz": 2048,
-                           "n_levels": 16, "extract_bsz": args.extract_bsz, "images_per_gpu": args.steps,
-                           "schedule": ("one image after the other" if args.no_overlap else
-                                        "bank extraction of image i+1 overlaps the fit of image i (2 bank buffers)"),
-                           "parallelism": f"image-sharded x{world}, one all-gather of denoised maps",
-                           "l2": "inputs larger than L2 (2.48 GB of views, 3.2 GB bank, 0.34 GB Adam state per image)"},
+                "config": workload_config(args, world),
+                "arm_notes": ("schedule: one image after the other" if args.no_overlap else
+                              "schedule: bank extraction of image i+1 overlaps the fit of image i (2 bank buffers)"),
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": dominant, "roofline_other": other}
         if e2e is not None:
             line["e2e"] = e2e
+        if world == 1 and not args.no_library_bar:
+            # the reference's op sequence through the vendor libraries on this same GPU
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import library_bar
+            del pipe
+            torch.cuda.empty_cache()
+            bar = library_bar.measure(dev, views=V, num_iters=args.num_iters)
+            fit_ours_s = hp2_ms / 1e3
+            bar["ours"] = {"fit_s_per_image_in_region": fit_ours_s, "hp1_s_per_image_in_region": hp1_ms / 1e3,
+                           "images_per_s": value}
+            bar["fit_wall_clock_ratio"] = bar["fit_s_per_image"] / fit_ours_s      # north_star target: >= 10
+            bar["images_per_s_ratio"] = {k: value / v for k, v in bar["images_per_s"].items()}
+            line["library_bar"] = bar
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(args)
         print(json.dumps(line))

@@ -21,6 +21,26 @@ from .._lib import DvtError
 from .vit_wrapper import PretrainedViTWrapper, _Block
 
 
+class CenterPadding(nn.Module):
+    """Zero-pads the trailing (spatial) dimensions of [B, C, ...] up to the next multiple of `multiple`, the surplus split
+    evenly with the odd pixel on the far side -- what the dense-task evaluation puts in front of a denoised backbone so
+    that any frame size maps onto whole patches (reference evaluation/eval_utils/misc.py:19-35)."""
+
+    def __init__(self, multiple: int):
+        super().__init__()
+        self.multiple = int(multiple)
+
+    def extra(self, size: int):
+        total = -size % self.multiple
+        return total // 2, total - total // 2
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        pads = []
+        for dim in range(x.dim() - 1, 1, -1):       # F.pad lists the last dimension first
+            pads.extend(self.extra(x.shape[dim]))
+        return F.pad(x, pads)
+
+
 class Denoiser(nn.Module):
     def __init__(self, noise_map_height: int = 37, noise_map_width: int = 37, feat_dim: int = 768,
                  vit: Optional[PretrainedViTWrapper] = None, enable_pe: bool = True, num_blocks: int = 1):

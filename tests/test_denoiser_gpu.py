@@ -64,3 +64,53 @@ def test_denoiser_behind_the_frozen_vit():
     assert got.shape == (2, 5, 6, C) and cls.shape == (2, C)
     assert _min_cos(got.cpu(), ref) > 0.999
     assert _min_cos(cls.cpu()[:, None], prefix[:, :1]) > 0.999
+
+
+def test_long_sequence_attention():
+    """N = 25 321 tokens (ViT at stride 4 on a 490 x 854 frame, make_video_demo.py:21-22,120): 198 key tiles per query tile
+    through the flash-attention kernel against torch SDPA in fp32 on the same GPU."""
+    from dvt import _lib, ops
+    B, N, heads = 1, 25321, 2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = (torch.randn(B, N, 3 * heads * 64, device="cuda", generator=g) * 1.5).bfloat16()
+    out = ops.attention(qkv, heads)
+    q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, heads * 64)
+    torch.cuda.synchronize()
+    assert _lib.device_error() == 0
+    assert (out.float() - ref).abs().max().item() < 3e-2
+    assert _min_cos(out, ref) > 0.9995
+
+
+def test_denoised_backbone_at_stride4_with_center_padding():
+    """What SURVEY.md row f-4 is for: a video-sized frame (480 x 850) centre-padded to patch multiples (490 x 854), the
+    frozen ViT at stride 4 -> 120 x 211 = 25 320 patch tokens, the learnable 37 x 37 position embedding resampled to that
+    grid, one denoiser block over the 25 320-token sequence.  Checker: the oracle (ViT + Denoiser restatement) evaluated in
+    fp32 on the same GPU (its explicit attention matrix needs ~30 GB: fine on a B200, not on a CPU box)."""
+    import dvt.models as DVT
+    from dvt import _lib
+    from oracle import denoiser as OD
+    from oracle import vit as OV
+    ident = "vit_small_patch14_dinov2.lvd142m"
+    cfg = OV.CONFIGS[ident]
+    vsd = OV.random_state_dict(cfg, seed=5)
+    vit = DVT.PretrainedViTWrapper(ident, stride=4, allow_random_init=True)
+    vit.model.load_state_dict(vsd)
+    C, hw = vit.n_output_dims, (37, 37)
+    sd = OD.random_state_dict(C, hw, 1, seed=6)
+    m = DVT.Denoiser(hw[0], hw[1], C, vit=vit, enable_pe=True)
+    m.load_state_dict({**sd, **{"vit." + k: v for k, v in vit.state_dict().items()}}, strict=True)
+    m = m.cuda().eval()
+    frame = torch.randn(1, 3, 480, 850, generator=torch.Generator().manual_seed(7))
+    x = DVT.CenterPadding(vit.patch_size)(frame).cuda()
+    assert x.shape == (1, 3, 490, 854)
+    with torch.no_grad():
+        got = m(x)
+        torch.cuda.synchronize()
+        assert got.shape == (1, 120, 211, C)
+        dev = lambda d: {k: v.cuda() for k, v in d.items()}  # noqa: E731
+        feats = OV.forward_intermediates(dev(vsd), cfg, x, [cfg.depth - 1], stride=4)[0]
+        ref = OD.forward(dev(sd), feats.permute(0, 2, 3, 1), hw)
+    assert _lib.device_error() == 0
+    mc = _min_cos(got, ref)
+    assert mc > 0.999, f"stride-4 denoised backbone: min per-patch cosine {mc}"

@@ -39,3 +39,20 @@ def test_denoiser_state_dict_contract():
         assert ours == ref
         m.load_state_dict(OD.random_state_dict(128, (5, 6), nb), strict=True)
     assert DVT.Denoiser(5, 6, 128, enable_pe=False).pos_embed is None
+
+
+def test_center_padding_matches_reference_rule():
+    """`dvt.models.CenterPadding` against the rule of evaluation/eval_utils/misc.py:19-35 (pad each spatial size up to the
+    next multiple, left = pad // 2, right = the rest), and against the reference class itself where it can be loaded."""
+    import math
+    import dvt.models as DVT
+    pad = DVT.CenterPadding(14)
+    for H, W in [(480, 850), (490, 854), (1, 15), (27, 28), (518, 518)]:
+        x = torch.arange(2 * 3 * H * W, dtype=torch.float32).reshape(2, 3, H, W)
+        y = pad(x)
+        nh, nw = math.ceil(H / 14) * 14, math.ceil(W / 14) * 14
+        t, l = (nh - H) // 2, (nw - W) // 2
+        assert y.shape == (2, 3, nh, nw)
+        assert torch.equal(y[:, :, t:t + H, l:l + W], x)
+        assert float(y.sum()) == float(x.sum())          # everything else is zero
+    assert pad(torch.ones(1, 2, 5, 6, 7)).shape == (1, 2, 14, 14, 14)   # any number of trailing dimensions
