@@ -41,6 +41,16 @@ int hashgrid_fwd(int n_levels, const float* scale, const uint32_t* res, const ui
                  const uint32_t* hashed, const float* table, const float* coords, int n, float* out, cudaStream_t st);
 int hashgrid_bwd(int n_levels, const float* scale, const uint32_t* res, const uint32_t* size, const uint32_t* offset,
                  const uint32_t* hashed, const float* coords, int n, const float* dout, float* gtable, cudaStream_t st);
+int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* out, const __nv_bfloat16* dout, const float* lse,
+                         __nv_bfloat16* dqkv, float* dq_acc, float* delta, int B, int N, int heads, cudaStream_t stream);
+int launch_layernorm_bwd(const float* x, const float* gamma, const float* dy, float* dx_accum, float* dgamma, float* dbeta,
+                         int rows, int C, float eps, cudaStream_t st);
+int launch_colsum(const void* in, bool bf16, int ld, int rows, int cols, float* out, cudaStream_t st);
+int launch_gelu(const __nv_bfloat16* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
+int launch_denoise_loss(const float* pred, const float* tgt, float* dpred, float* losses, int rows, int C, float grad_scale,
+                        cudaStream_t st);
+int launch_adamw(float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1, double beta2, double eps,
+                 double weight_decay, long long step, cudaStream_t st);
 const char* last_error();
 extern int g_debug_impl_override;
 int g_debug_impl_override = -1;
@@ -126,6 +136,60 @@ int dvt_attention_fwd(const void* qkv_bf16, void* out_bf16, int B, int N, int he
   if (impl < 0) impl = default_gemm_impl();
   return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16),
                           B, N, heads, reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+/* ---- stage-2 training operators ---- */
+int dvt_attention_fwd_lse(const void* qkv_bf16, void* out_bf16, float* lse, int B, int N, int heads, void* stream) {
+  DVT_REQUIRE(qkv_bf16 && out_bf16 && lse, "dvt_attention_fwd_lse: null pointer");
+  return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                          B, N, heads, reinterpret_cast<cudaStream_t>(stream), 0, lse);
+}
+int dvt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
+                      float* dq_workspace, float* delta_workspace, int B, int N, int heads, void* stream) {
+  return launch_attention_bwd(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<const __nv_bfloat16*>(out_bf16),
+                              reinterpret_cast<const __nv_bfloat16*>(dout_bf16), lse, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16),
+                              dq_workspace, delta_workspace, B, N, heads, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_layernorm_bwd(const float* x, const float* gamma, const float* dy, float* dx_accum, float* dgamma, float* dbeta,
+                      int rows, int C, float eps, void* stream) {
+  return launch_layernorm_bwd(x, gamma, dy, dx_accum, dgamma, dbeta, rows, C, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_colsum(const void* in, int dtype, int ld, int rows, int cols, float* out_accum, void* stream) {
+  return launch_colsum(in, dtype == DVT_DTYPE_BF16, ld, rows, cols, out_accum, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_gelu(const void* in_bf16, void* out_bf16, size_t n, void* stream) {
+  return launch_gelu(reinterpret_cast<const __nv_bfloat16*>(in_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), n,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_gemm_bf16_bwd(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, void* out,
+                      int ldo, int out_dtype, int splits, const void* gelu_preact_bf16, int ld_preact, void* stream) {
+  DVT_REQUIRE(A && B && out, "dvt_gemm_bf16_bwd: null pointer");
+  GemmEpi e;
+  e.out = out;
+  e.ldo = ldo;
+  if (splits > 1) {
+    DVT_REQUIRE(out_dtype == DVT_DTYPE_F32 && !gelu_preact_bf16, "dvt_gemm_bf16_bwd: split-K needs plain fp32 output");
+    e.out_mode = OUT_F32_ATOMIC;
+  } else {
+    e.out_mode = out_dtype == DVT_DTYPE_BF16 ? OUT_BF16 : OUT_F32;
+  }
+  if (gelu_preact_bf16) {
+    e.mask = reinterpret_cast<const __nv_bfloat16*>(gelu_preact_bf16);
+    e.ldmask = ld_preact;
+    e.mask_mode = 1;
+  }
+  GemmShape s{M, N, K, splits < 1 ? 1 : splits};
+  s.a_mn = a_mn;
+  s.b_mn = b_mn;
+  return launch_gemm_tn(A, lda, B, ldb, TMAP_BF16, s, e, reinterpret_cast<cudaStream_t>(stream), eff_impl());
+}
+int dvt_denoise_loss(const float* pred, const float* target, float* dpred, float* losses3, int rows, int C, float grad_scale,
+                     void* stream) {
+  return launch_denoise_loss(pred, target, dpred, losses3, rows, C, grad_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_adamw(float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1, double beta2, double eps,
+              double weight_decay, long long step, void* stream) {
+  return launch_adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dvt_im2col(const void* x, int x_dtype, void* out_bf16, int B, int H, int W, int P, int S, void* stream) {

@@ -75,7 +75,7 @@ __device__ __forceinline__ float ex2_fma(float x) {
 template <int MODE>
 __global__ void __launch_bounds__(MODE == 2 ? 320 : ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int C,
-                    float scale_log2e) {
+                    float scale_log2e, float* __restrict__ lse) {
   constexpr bool LAZY = MODE >= 1;
   constexpr bool PAIR = MODE == 2;
   constexpr bool POLY = MODE == 3;   // MODE 3 = MODE 1 with a quarter of the exponentials on the FMA pipe
@@ -408,6 +408,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       const float inv = 1.0f / l_run;
       const int q = q0 + row;
       if (q < N) {
+        // log-sum-exp of the scaled scores in the log2 domain (training: the backward kernel recomputes P from it):
+        // P[q, k] = exp2(s[q, k] * scale_log2e - lse[q]), layout [B, heads, N]
+        if (lse) lse[((size_t)b * gridDim.y + head) * N + q] = m_run + log2f(l_run);
         __nv_bfloat16* dst = out + ((size_t)b * N + q) * C + head * ATT_D;
 #pragma unroll
         for (int d8 = 0; d8 < 8; ++d8) {
@@ -600,11 +603,12 @@ __global__ void attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv, __n
 }  // namespace
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t stream,
-                     int impl) {
+                     int impl, float* lse) {
   const int C = heads * ATT_D;
   DVT_REQUIRE(B > 0 && N > 0 && heads > 0, "attention: bad shape B=%d N=%d heads=%d", B, N, heads);
   const float scale = 0.125f;  // 64^-0.5
   if (impl == 1) {
+    DVT_REQUIRE(lse == nullptr, "attention (simt debug): the log-sum-exp output needs the tcgen05 kernel");
     DVT_REQUIRE(N <= 12000, "attention (simt debug): N=%d too large", N);
     dim3 grid(N, heads, B);
     attention_simt_kernel<<<grid, 32, N * sizeof(float), stream>>>(qkv, out, N, C, scale);
@@ -624,16 +628,17 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     if (v && v[0] >= '0' && v[0] <= '3') mode = v[0] - '0';
     attr_set = true;
   }
+  DVT_REQUIRE(lse == nullptr || mode == 1, "attention: the log-sum-exp output is implemented by DVT_ATTN_MODE=1 (default)");
   CUtensorMap tm;
   int rc = make_tmap_3d(&tm, qkv, TMAP_BF16, (uint64_t)3 * C, (uint64_t)N, (uint64_t)B, (uint64_t)3 * C * 2,
                         (uint64_t)N * 3 * C * 2, ATT_D, ATT_BK);
   if (rc) return rc;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
   const float sl2 = scale * 1.4426950408889634f;
-  if (mode == 3) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
-  else if (mode == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<2>, grid, dim3(320), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
-  else if (mode == 1) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<1>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
-  else DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<0>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2));
+  if (mode == 3) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<2>, grid, dim3(320), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 1) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<1>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
+  else DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<0>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;

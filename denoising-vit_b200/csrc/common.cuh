@@ -190,6 +190,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): size and both addresses multiples of 16 bytes
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -327,6 +335,11 @@ __device__ __forceinline__ float fast_erf(float x) {
   return copysignf(r, x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+
+// d/dx gelu_erf(x) = Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_grad(float x) {
+  return fmaf(x * 0.3989422804014327f, __expf(-0.5f * x * x), 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f)));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

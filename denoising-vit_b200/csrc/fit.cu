@@ -552,6 +552,112 @@ fit_adam_table_kernel(TableBufs tb, size_t nvec, const AdamScalars* __restrict__
   }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// EXPERIMENT (DVT_FIT_SWEEP_TMA=1; not the default): the same sweep staged through shared memory by bulk async copies
+// (TMA, cp.async.bulk).  ONE thread per CTA keeps three 52 KB chunks (p, m, v and the two stamp arrays of 512 table
+// entries) in flight per SM through an mbarrier ring of four stages while 512 threads run the Adam arithmetic out of
+// shared memory and write the results back with coalesced 16-byte stores.  Idea: memory-level parallelism independent of
+// the thread count, so that a few dozen SMs could saturate HBM.  Measured (profiles/r2b_sweep_tma_experiment.txt): beside
+// the GEMM chain it moves ~55 GB/s per SM against ~79 GB/s of the plain-load kernel -- either way ~100-150 KB in flight
+// per SM and ~1.5-2.5 us of loaded latency, i.e. Little's law caps a 40-SM sweep near half of the HBM rate; only the whole
+// GPU (148 SMs x ~90 KB) holds the ~13 MB in flight that 6.5 TB/s needs.  Same adam1() arithmetic, same stamp rules:
+// bit-identical results (tests/test_fit_gpu.py::test_sweep_kernels_agree).
+// Chunks are dealt round-robin (chunk c -> CTA c % grid), i.e. all CTAs advance one contiguous front together.
+// ----------------------------------------------------------------------------------------------------
+constexpr int SW_ENT = 512;                       // table entries per chunk
+constexpr int SW_FLOATS = SW_ENT * FIT_F;         // 4096 floats = 16 KB per array and chunk
+constexpr int SW_STAGES = 4;
+constexpr int SW_THREADS = 512;
+struct SweepStage {
+  float p[SW_FLOATS], m[SW_FLOATS], v[SW_FLOATS];
+  uint32_t stamp[SW_ENT], stamp_z[SW_ENT];
+};
+constexpr size_t SW_SMEM = SW_STAGES * sizeof(SweepStage) + SW_STAGES * sizeof(uint64_t) + 128;
+static_assert(sizeof(SweepStage) % 128 == 0, "stage size keeps the 16-byte alignment of bulk copies");
+static_assert(SW_SMEM <= 227 * 1024, "sweep stages exceed shared memory");
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+fit_adam_table_tma_kernel(TableBufs tb, uint32_t n_entries, const AdamScalars* __restrict__ sc,
+                          const int* __restrict__ step_base, int step_off, float wd) {
+  extern __shared__ uint8_t sw_smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sw_smem_raw) + 127) & ~uintptr_t(127));
+  SweepStage* stg = reinterpret_cast<SweepStage*>(base);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + SW_STAGES * sizeof(SweepStage));
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < SW_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
+  pdl_trigger();
+  const int step = *step_base + step_off;
+  const int src = step & 1, slot = mod3(step), slot_prev = mod3(step + 2);
+  const float* __restrict__ p = DVT_SEL2(tb.p, src);
+  const float* __restrict__ m = DVT_SEL2(tb.m, src);
+  const float* __restrict__ v = DVT_SEL2(tb.v, src);
+  float4* __restrict__ po = reinterpret_cast<float4*>(DVT_SEL2(tb.p, src ^ 1));
+  float4* __restrict__ mo = reinterpret_cast<float4*>(DVT_SEL2(tb.m, src ^ 1));
+  float4* __restrict__ vo = reinterpret_cast<float4*>(DVT_SEL2(tb.v, src ^ 1));
+  const float4* __restrict__ g = reinterpret_cast<const float4*>(DVT_SEL3(tb.g, slot));
+  const uint32_t* __restrict__ stamp = DVT_SEL3(tb.stamp, slot);
+  float4* __restrict__ gz = reinterpret_cast<float4*>(DVT_SEL3(tb.g, slot_prev));
+  const uint32_t* __restrict__ stamp_z = DVT_SEL3(tb.stamp, slot_prev);
+  const AdamScalars s = sc[step];
+  const uint32_t mark = (uint32_t)step + 1u;
+  const uint32_t mark_z = step > 0 ? (uint32_t)step : 0xffffffffu;  // stamp of step - 1 (never matches at step 0)
+  const uint32_t n_chunks = (n_entries + SW_ENT - 1) / SW_ENT;
+
+  auto issue = [&](uint32_t k) {  // thread 0: bulk loads of this CTA's k-th chunk into stage k % SW_STAGES
+    const uint32_t c = blockIdx.x + k * gridDim.x;
+    if (c >= n_chunks) return;
+    SweepStage& st = stg[k % SW_STAGES];
+    uint64_t* bar = &full[k % SW_STAGES];
+    const uint32_t e0 = c * SW_ENT, ne = min((uint32_t)SW_ENT, n_entries - e0);
+    const uint32_t bp = ne * FIT_F * 4, bs = ne * 4;  // entries per level are multiples of 8: both multiples of 32 B
+    mbar_expect_tx(bar, 3 * bp + 2 * bs);
+    bulk_load_1d(st.p, p + (size_t)e0 * FIT_F, bp, bar);
+    bulk_load_1d(st.m, m + (size_t)e0 * FIT_F, bp, bar);
+    bulk_load_1d(st.v, v + (size_t)e0 * FIT_F, bp, bar);
+    bulk_load_1d(st.stamp, stamp + e0, bs, bar);
+    bulk_load_1d(st.stamp_z, stamp_z + e0, bs, bar);
+  };
+  if (tid == 0)
+    for (uint32_t k = 0; k + 1 < SW_STAGES; ++k) issue(k);
+
+  for (uint32_t k = 0;; ++k) {
+    const uint32_t c = blockIdx.x + k * gridDim.x;
+    if (c >= n_chunks) break;
+    // refill the stage that was consumed in iteration k-1 (all its readers passed the __syncthreads below)
+    if (tid == 0) issue(k + SW_STAGES - 1);
+    const SweepStage& st = stg[k % SW_STAGES];
+    mbar_wait(&full[k % SW_STAGES], (k / SW_STAGES) & 1u, 0x51);
+    const uint32_t e0 = c * SW_ENT, ne = min((uint32_t)SW_ENT, n_entries - e0);
+    const size_t f0 = (size_t)e0 * 2;            // first float4 of the chunk
+    const float4* sp = reinterpret_cast<const float4*>(st.p);
+    const float4* sm = reinterpret_cast<const float4*>(st.m);
+    const float4* sv = reinterpret_cast<const float4*>(st.v);
+#pragma unroll
+    for (int u = 0; u < (SW_ENT * 2) / SW_THREADS; ++u) {
+      const uint32_t i = tid + u * SW_THREADS;   // float4 index inside the chunk; entry = i / 2
+      if (i < ne * 2) {
+        const bool touched = st.stamp[i >> 1] == mark;
+        const bool stale = st.stamp_z[i >> 1] == mark_z;
+        float4 pp = sp[i], mm = sm[i], vv = sv[i];
+        float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (touched) gg = __ldcg(g + f0 + i);
+        if (stale) gz[f0 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        adam1(pp.x, mm.x, vv.x, gg.x, wd, s.step_size, s.inv_bc2_sqrt);
+        adam1(pp.y, mm.y, vv.y, gg.y, wd, s.step_size, s.inv_bc2_sqrt);
+        adam1(pp.z, mm.z, vv.z, gg.z, wd, s.step_size, s.inv_bc2_sqrt);
+        adam1(pp.w, mm.w, vv.w, gg.w, wd, s.step_size, s.inv_bc2_sqrt);
+        po[f0 + i] = pp; mo[f0 + i] = mm; vo[f0 + i] = vv;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // small params: one flat buffer; [g_lo, g_hi) is G, [r_lo, r_hi) the residual MLP, the rest the field MLP.
 __global__ void fit_adam_small_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                       float4* __restrict__ g, float* __restrict__ wsplit, int nvec, int g_lo,
@@ -599,11 +705,12 @@ __global__ void fit_transpose_kernel(const float* __restrict__ in, float* __rest
   }
 }
 
-__global__ void fit_split_kernel(const float* __restrict__ p, float* __restrict__ wsplit, size_t n) {
+// TF32 hi / lo operand planes of n parameters: wsplit[e] = hi, wsplit[plane + e] = lo
+__global__ void fit_split_kernel(const float* __restrict__ p, float* __restrict__ wsplit, size_t n, size_t plane) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const float v = p[e], hi = tf32_hi(v);
     wsplit[e] = hi;
-    wsplit[n + e] = v - hi;
+    wsplit[plane + e] = v - hi;
   }
 }
 
@@ -641,6 +748,7 @@ struct Fit {
   bool pdl = true;                             // programmatic dependent launch along the kernel chains of a step
   bool pipe[2] = {true, true};                 // software-pipelined table sweep in phase 1 / 2 (see fit_enqueue_step)
   int sweep_ctas[2] = {0, 0};                  // persistent sweep CTAs in phase 1 / 2 (0 = many small CTAs)
+  bool sweep_tma = false;                      // DVT_FIT_SWEEP_TMA=1: persistent sweep = the TMA-staged kernel (experiment)
   float *sp = nullptr, *sm = nullptr, *sv = nullptr, *sg = nullptr;
   float* wsplit = nullptr;  // [2][n_small] TF32 hi / lo planes of the small params (x3 GEMM operands)
   // activations: GEMM operands are stored as two fp32 planes (hi, lo), plane stride = bsz * ld
@@ -738,6 +846,10 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
     }
     //   DVT_FIT_PDL=0               plain stream-ordered launches (no programmatic dependent launch)
     //   DVT_FIT_RES_TF32=1          residual-MLP GEMMs in plain TF32 instead of 3xTF32 (experiment; not the default)
+    //   DVT_FIT_SWEEP_TMA=1         persistent sweep CTAs use the TMA-staged kernel instead of plain loads (measured slower
+    //                               beside the chain: profiles/r2b_sweep_tma_experiment.txt; kept as a tested experiment)
+    const char* tm = getenv("DVT_FIT_SWEEP_TMA");
+    f->sweep_tma = tm && tm[0] == '1';
     const char* rt = getenv("DVT_FIT_RES_TF32");
     f->res_x3 = (rt && rt[0] == '1') ? 2 : 1;
     const char* pd = getenv("DVT_FIT_PDL");
@@ -890,6 +1002,9 @@ int fit_set_param(Fit* f, const char* name_c, const float* src, size_t numel, cu
     DVT_CUDA_OK(cudaGetLastError());
   } else {
     DVT_CUDA_OK(cudaMemcpyAsync(f->sp + s->off, src, numel * 4, cudaMemcpyDefault, st));
+    // the GEMMs read the weights as TF32 hi / lo planes: keep them current (fit_query / fit_residual may follow directly)
+    fit_split_kernel<<<64, 256, 0, st>>>(f->sp + s->off, f->wsplit + s->off, numel, (size_t)f->n_small);
+    DVT_CUDA_OK(cudaGetLastError());
   }
   return fit_before_caller(f, caller);
 }
@@ -897,9 +1012,10 @@ int fit_set_param(Fit* f, const char* name_c, const float* src, size_t numel, cu
 int fit_get_param(Fit* f, const char* name_c, float* dst, size_t numel) {
   const std::string name(name_c);
   DVT_CUDA_OK(cudaDeviceSynchronize());
-  if (name == "table") {
+  if (name == "table" || name == "table.next") {  // "table.next": the buffer a sweep writes (dvt_fit_sweep_once, tests)
     DVT_REQUIRE(numel == f->n_table, "fit_get_param: table size mismatch");
-    DVT_CUDA_OK(cudaMemcpy(dst, f->tb.p[f->cur_host & 1], numel * 4, cudaMemcpyDefault));
+    const int b = (f->cur_host & 1) ^ (name == "table" ? 0 : 1);
+    DVT_CUDA_OK(cudaMemcpy(dst, f->tb.p[b], numel * 4, cudaMemcpyDefault));
     return DVT_OK;
   }
   Seg* s = nullptr;
@@ -975,6 +1091,8 @@ int fit_init_params(Fit* f, uint64_t seed, cudaStream_t caller) {
     FIT_RC0(launch(f->sp + l.b->off, (size_t)l.b->rows, l.tid + 1, 0, bound));
   }
   FIT_RC0(launch(f->sp + f->G.off, (size_t)f->hw * f->C, 11, 1, 0.02f, f->C, f->hw));
+  fit_split_kernel<<<256, 256, 0, st>>>(f->sp, f->wsplit, (size_t)f->n_small, (size_t)f->n_small);
+  DVT_CUDA_OK(cudaGetLastError());
   return fit_before_caller(f, caller);
 }
 
@@ -1118,7 +1236,7 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
   DVT_CUDA_OK(cudaMemsetAsync(f->sm, 0, (size_t)f->n_small * 4, st));
   DVT_CUDA_OK(cudaMemsetAsync(f->sv, 0, (size_t)f->n_small * 4, st));
   DVT_CUDA_OK(cudaMemsetAsync(f->sg, 0, (size_t)f->n_small * 4, st));
-  fit_split_kernel<<<256, 256, 0, st>>>(f->sp, f->wsplit, (size_t)f->n_small);
+  fit_split_kernel<<<256, 256, 0, st>>>(f->sp, f->wsplit, (size_t)f->n_small, (size_t)f->n_small);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   if (validate) return fit_check(f);
@@ -1178,7 +1296,22 @@ static void fit_sweep_geometry(const Fit* f, bool phase2, int* grid, int* block)
   else { *grid = num_sms() * 8; *block = 256; }
 }
 
+static int fit_launch_sweep_tma(Fit* f, int ctas, int step_off, cudaStream_t st, bool pdl) {
+  static bool prepared = false;
+  if (!prepared) {
+    DVT_CUDA_OK(cudaFuncSetAttribute(fit_adam_table_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM));
+    prepared = true;
+  }
+  DVT_CUDA_OK(launch_k(pdl, fit_adam_table_tma_kernel, dim3(ctas), dim3(SW_THREADS), SW_SMEM, st, f->tb,
+                       (uint32_t)(f->n_table / FIT_F), f->sc_main, f->step_base, step_off, f->wd));
+  DVT_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return DVT_OK;
+}
+
 static int fit_launch_sweep(Fit* f, int step_off, bool phase2, cudaStream_t st) {
+  if (f->sweep_tma && f->sweep_ctas[phase2 ? 1 : 0] > 0)
+    return fit_launch_sweep_tma(f, f->sweep_ctas[phase2 ? 1 : 0], step_off, st, f->pdl);
   int sg_ = 0, sb_ = 0;
   fit_sweep_geometry(f, phase2, &sg_, &sb_);
   DVT_CUDA_OK(launch_k(f->pdl, fit_adam_table_kernel, dim3(sg_), dim3(sb_), 0, st, f->tb, f->n_table / 4, f->sc_main,
@@ -1413,7 +1546,11 @@ int fit_sweep_once(Fit* f, int ctas, cudaStream_t st) {
   // (no device read-back here: a blocking copy per call would put ~20 us of host latency between back-to-back launches
   //  and into every event-timed measurement; the host mirror of the step counter is enough for the bounds check)
   DVT_REQUIRE(f->cur_host <= f->num_iters, "fit_sweep_once: step counter %d beyond the schedule", f->cur_host);
-  const int grid = ctas > 0 ? std::min(ctas, num_sms()) : num_sms() * 8, block = ctas > 0 ? 1024 : 256;
+  // ctas > 0: persistent CTAs as in the pipelined schedule (TMA-staged kernel unless DVT_FIT_SWEEP_TMA=0);
+  // ctas < 0: -ctas persistent CTAs of the plain-load kernel; 0: the many-small-CTA geometry of the sequential schedule
+  if (ctas > 0 && f->sweep_tma) return fit_launch_sweep_tma(f, std::min(ctas, num_sms()), 0, st, false);
+  const int n = ctas < 0 ? -ctas : ctas;
+  const int grid = n > 0 ? std::min(n, num_sms()) : num_sms() * 8, block = n > 0 ? 1024 : 256;
   fit_adam_table_kernel<<<grid, block, 0, st>>>(f->tb, f->n_table / 4, f->sc_main, f->step_base, 0, f->wd);
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -375,8 +375,13 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint2 hb = *reinterpret_cast<const uint2*>(e.mask + (size_t)m * e.ldmask + n);
               const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
               const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
-              x.x = __low2float(h01) > 0.f ? x.x : 0.f; x.y = __high2float(h01) > 0.f ? x.y : 0.f;
-              x.z = __low2float(h23) > 0.f ? x.z : 0.f; x.w = __high2float(h23) > 0.f ? x.w : 0.f;
+              if (e.mask_mode == 1) {  // GELU backward: the mask tensor is the forward pre-activation
+                x.x *= gelu_grad(__low2float(h01)); x.y *= gelu_grad(__high2float(h01));
+                x.z *= gelu_grad(__low2float(h23)); x.w *= gelu_grad(__high2float(h23));
+              } else {
+                x.x = __low2float(h01) > 0.f ? x.x : 0.f; x.y = __high2float(h01) > 0.f ? x.y : 0.f;
+                x.z = __low2float(h23) > 0.f ? x.z : 0.f; x.w = __high2float(h23) > 0.f ? x.w : 0.f;
+              }
             }
             if (e.alpha != 1.0f) { x.x *= e.alpha; x.y *= e.alpha; x.z *= e.alpha; x.w *= e.alpha; }
             if (e.out_mode == OUT_F32_RESID) {

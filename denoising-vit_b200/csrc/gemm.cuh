@@ -25,6 +25,8 @@ struct GemmEpi {
   const __nv_bfloat16* mask = nullptr;  // optional [M, ldmask]: v *= (mask[m, n] > 0)   (ReLU backward)
   const float* mask_f32 = nullptr;      // same, fp32 mask tensor
   int ldmask = 0;
+  int mask_mode = 0;                  // bf16 `mask` only: 0 = gate (v *= mask > 0), 1 = v *= gelu'(mask)  (GELU backward:
+                                      // `mask` holds the pre-activation of the forward pass)
   float alpha = 1.0f;                 // v *= alpha (after activation / mask)
   // post-stage (coalesced)
   int out_mode = OUT_BF16;
@@ -62,7 +64,7 @@ __device__ __forceinline__ float epi_pre(const GemmEpi& e, int m, int n, float a
   else if (e.act == ACT_RELU) v = fmaxf(v, 0.0f);
   if (e.mask) {
     float h = __bfloat162float(e.mask[(size_t)m * e.ldmask + n]);
-    v = h > 0.0f ? v : 0.0f;
+    v = e.mask_mode == 1 ? v * gelu_grad(h) : (h > 0.0f ? v : 0.0f);
   }
   if (e.mask_f32) v = e.mask_f32[(size_t)m * e.ldmask + n] > 0.0f ? v : 0.0f;
   return v * e.alpha;

@@ -25,7 +25,7 @@ int launch_layernorm(const float* x, int ldx, const float* gamma, const float* b
 int launch_im2col(const void* x, bool x_bf16, __nv_bfloat16* out, int B, int H, int W, int P, int S, int h, int w,
                   int Kp, cudaStream_t stream);
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N, int heads, cudaStream_t stream,
-                     int impl);
+                     int impl, float* lse = nullptr);
 __global__ void strip_copy_kernel(const float*, int, float*, int, int, int, int, int);
 __global__ void prefix_rows_kernel(const float*, float*, int, int, int, int);
 __global__ void swiglu_kernel(const __nv_bfloat16*, __nv_bfloat16*, size_t, int);

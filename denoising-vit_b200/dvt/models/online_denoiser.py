@@ -6,8 +6,11 @@ timm's `resample_abs_pos_embed` when the grid differs), then the denoiser block(
 LayerNorm -> QKV GEMM -> flash attention -> out-proj GEMM (+ residual) -> LayerNorm -> fc1 GEMM + GELU -> fc2 GEMM
 (+ residual), no LayerScale (`init_values=None`).
 
-INFERENCE ONLY: the stage-2 training step needs the backward of these kernels and is not built; the
-forward therefore runs under `torch.no_grad()` semantics and raises if a gradient is requested."""
+TRAINING (reference main_denoiser.py:213-220): when gradients are enabled and the denoiser's parameters
+require them, every block runs as ONE autograd node (`dvt.train_ops.block_forward`) whose backward is hand-written too:
+flash-attention backward on tcgen05, LayerNorm / GELU / bias gradients, bf16 data- and weight-gradient GEMMs that read
+weights and activations in place as MN-major operands.  The position embedding (and its resampling, when the grid
+differs) stays an ordinary torch op in the graph, so `pos_embed.grad` comes out of autograd."""
 from __future__ import annotations
 
 from typing import Dict, Optional
@@ -16,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import ops, train_ops
 from .._lib import DvtError
 from .vit_wrapper import PretrainedViTWrapper, _Block
 
@@ -98,12 +101,24 @@ class Denoiser(nn.Module):
         return x
 
     # ---- forward (online_denoiser.py:62-104) ----------------------------------------------------------------------
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self.denoiser.parameters())
+                                            or (self.pos_embed is not None and self.pos_embed.requires_grad))
+
+    def _pos_train(self, h: int, w: int) -> Optional[torch.Tensor]:
+        """Position embedding inside the autograd graph (training): the parameter itself, or its bicubic resampling."""
+        if self.pos_embed is None:
+            return None
+        gh, gw = self.noise_map_size
+        if (h, w) == (gh, gw):
+            return self.pos_embed.float()
+        g = self.pos_embed.float().reshape(1, gh, gw, -1).permute(0, 3, 1, 2)
+        g = F.interpolate(g, size=(h, w), mode="bicubic", antialias=True)
+        return g.permute(0, 2, 3, 1).reshape(1, h * w, -1)
+
     def forward(self, x, return_dict=False, return_channel_first=False, return_class_token=False, norm=True):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.denoiser.parameters()) and x.requires_grad:
-            raise DvtError("dvt_b200 Denoiser is inference only (the stage-2 training step is not built): wrap the call in "
-                           "torch.no_grad()")
+        class_tokens = None
         with torch.no_grad():
-            class_tokens = None
             if self.vit is not None:
                 outs = self.vit.get_intermediate_layers(x, n=[self.vit.last_layer_index],
                                                         return_prefix_tokens=return_class_token, norm=norm)
@@ -115,17 +130,29 @@ class Denoiser(nn.Module):
             else:
                 if not x.is_cuda:
                     raise DvtError("dvt_b200 Denoiser needs CUDA tensors (no CPU fallback)")
-                original_feats = x.clone()
-            b, h, w, c = x.shape
+                original_feats = x.detach().clone()
+        b, h, w, c = x.shape
+        if self._wants_grad():
+            # ---- training: one autograd node per block ----
             t = x.reshape(b, h * w, c).float()
-            pos = self._pos(h, w)
-            t = (t + pos) if pos is not None else t.clone()
-            t = t.reshape(b * h * w, c).contiguous()
+            pos = self._pos_train(h, w)
+            if pos is not None:
+                t = t + pos
+            t = t.reshape(b * h * w, c)
             for blk in self._blocks():
-                t = self._block_forward(t, blk, b, h * w)
+                t = train_ops.block_forward(t, blk, self.num_heads, b)
             out = t.reshape(b, h, w, c)
-            if return_channel_first:
-                out = out.permute(0, 3, 1, 2)
+        else:
+            with torch.no_grad():
+                t = x.reshape(b, h * w, c).float()
+                pos = self._pos(h, w)
+                t = (t + pos) if pos is not None else t.clone()
+                t = t.reshape(b * h * w, c).contiguous()
+                for blk in self._blocks():
+                    t = self._block_forward(t, blk, b, h * w)
+                out = t.reshape(b, h, w, c)
+        if return_channel_first:
+            out = out.permute(0, 3, 1, 2)
         if return_dict:
             return {"denoised_feats": out, "original_feats": original_feats.detach(),
                     "class_tokens": class_tokens.detach() if class_tokens is not None else None}

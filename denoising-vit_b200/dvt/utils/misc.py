@@ -47,3 +47,21 @@ def feature_paths(args, filename: str):
 def check_if_file_exists(args, filename: str) -> bool:
     raw_path, den_path = feature_paths(args, filename)
     return os.path.isfile(raw_path) and os.path.isfile(den_path)
+
+
+def cosine_schedule(it: int, base_value: float, final_value: float, total_iters: int, warmup_iters: int = 0,
+                    start_warmup_value: float = 0.0) -> float:
+    """Value at iteration `it` of the stage-2 schedule (reference `CosineScheduler`, dvt/utils/misc.py:211-241): a linear
+    ramp of `warmup_iters` points from start_warmup_value to base_value INCLUSIVE (np.linspace), then a half cosine over
+    the remaining iterations that reaches final_value only after the last one; final_value from total_iters on."""
+    if it >= total_iters:
+        return final_value
+    if it < warmup_iters:
+        return float(np.linspace(start_warmup_value, base_value, warmup_iters)[it])
+    n = total_iters - warmup_iters
+    return float(final_value + 0.5 * (base_value - final_value) * (1 + np.cos(np.pi * (it - warmup_iters) / n)))
+
+
+def apply_optim_scheduler(optimizer, lr: float):
+    for group in optimizer.param_groups:
+        group["lr"] = lr

@@ -195,6 +195,41 @@ int dvt_fit_residual(dvt_fit_t* h, const float* raw, int n, float* out, void* st
 int dvt_fit_sweep_once(dvt_fit_t* h, int ctas, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Stage 2: training step of the generalizable denoiser (reference main_denoiser.py:197-221 -- forward of
+ * `Denoiser` (dvt/models/online_denoiser.py:62-104: one pre-LN timm Block), MSE + (1 - cosine) loss, loss.backward(),
+ * torch.optim.AdamW.step()).  Unit operators; dvt.models.Denoiser composes them into an autograd function, the forward
+ * GEMMs are dvt_gemm_tn / dvt_gemm_tn_residual above.
+ * ------------------------------------------------------------------------------------------------------- */
+/* dvt_attention_fwd that also writes lse f32 [B, heads, N]: log2-domain log-sum-exp of the scaled scores. */
+int dvt_attention_fwd_lse(const void* qkv_bf16, void* out_bf16, float* lse, int B, int N, int heads, void* stream);
+/* Flash-attention backward (replaces autograd through F.scaled_dot_product_attention in timm Attention): dqkv bf16
+ * [B, N, 3*heads*64] from qkv, the forward output `out`, its gradient `dout` (bf16 [B, N, heads*64]) and lse.
+ * Workspaces: dq_workspace f32 [B, N, heads*64], delta_workspace f32 [B, heads, N]. */
+int dvt_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, void* dqkv_bf16,
+                      float* dq_workspace, float* delta_workspace, int B, int N, int heads, void* stream);
+/* LayerNorm backward: dx_accum [rows, C] += d/dx, dgamma / dbeta [C] += their gradients (all f32; x is the LN input). */
+int dvt_layernorm_bwd(const float* x, const float* gamma, const float* dy, float* dx_accum, float* dgamma, float* dbeta,
+                      int rows, int C, float eps, void* stream);
+/* out_accum[n] += sum_m in[m, n]  (bias gradients); in: bf16 or f32 [rows, cols] with row pitch ld. */
+int dvt_colsum(const void* in, int dtype, int ld, int rows, int cols, float* out_accum, void* stream);
+/* dvt_gemm_bf16_ex for the backward GEMMs: data gradients (b_mn = 1: the weight is read in its [out, in] storage),
+ * weight gradients (a_mn = b_mn = 1: activations read in their [rows, features] storage, split-K over the rows with
+ * f32 atomics into a zeroed buffer), and optionally the GELU derivative fused into the epilogue: out = (A.B^T) *
+ * gelu'(gelu_preact[m, n]) (replaces autograd through nn.GELU). */
+int dvt_gemm_bf16_bwd(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K, void* out,
+                      int ldo, int out_dtype, int splits, const void* gelu_preact_bf16, int ld_preact, void* stream);
+/* out = gelu(in), erf form, bf16, n % 8 == 0  (forward of the MLP activation when the pre-activation must be kept). */
+int dvt_gelu(const void* in_bf16, void* out_bf16, size_t n, void* stream);
+/* Loss of main_denoiser.py:214-217 and its gradient: losses3 = (l2 + cos, l2 = mse, cos = 1 - mean cosine similarity);
+ * dpred (optional) = grad_scale * d(l2 + cos)/dpred.  pred, target, dpred f32 [rows, C]. */
+int dvt_denoise_loss(const float* pred, const float* target, float* dpred, float* losses3, int rows, int C, float grad_scale,
+                     void* stream);
+/* torch.optim.AdamW step (main_denoiser.py:176-180,220) over one flat f32 buffer of n (multiple of 4) parameters;
+ * step counts from 1. */
+int dvt_adamw(float* p, const float* g, float* m, float* v, size_t n, double lr, double beta1, double beta2, double eps,
+              double weight_decay, long long step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * view generation (the step in front of HP-1)
  * Replaces RandomResizedCropFlip.forward (dvt/dataset/transform.py:39-76) + the 8-worker DataLoader of
  * main_img_denoising.py:277-310.  image: device f32 [3, H, W] (already normalised).  boxes_host: HOST int32 [V, 4] =

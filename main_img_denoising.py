@@ -89,7 +89,8 @@ def get_args(argv=None):
     p.add_argument("--seed", type=int, default=0)
     # B200 extensions (not reference flags)
     p.add_argument("--collate_out", type=str, default=None,
-                   help="rank 0 saves the all-gathered stack of denoised maps [N, h, w, C] (+ the image list) here (.pt)")
+                   help="rank 0 saves the all-gathered stacks of raw and denoised maps [N, h, w, C] (+ the image list) here "
+                        "(.pt); main_denoiser.py --collated trains from it")
     p.add_argument("--sequential", action="store_true", help="one image after the other (no pipelining over images)")
     args = p.parse_args(argv)
     assert os.path.exists(args.img_path), f"Image not found: {args.img_path}"
@@ -189,7 +190,7 @@ def main(args):
             writer.submit(raw_path, den_path, out["raw"], out["denoised_feats"])
             print(f"Saving denoised features to {den_path} and raw features to {raw_path}")
         if keep_maps:
-            maps.append(out["denoised_feats"][0])
+            maps.append(torch.stack([out["raw"], out["denoised_feats"][0]]))     # [2, h, w, C]: the stage-2 training pair
         coords_of.pop(i, None)
         now = time.time()
         state["done"] += 1
@@ -206,13 +207,13 @@ def main(args):
         writer.close()
     if keep_maps:
         local_maps = (torch.stack(maps) if maps else
-                      torch.empty((0, pipe.h, pipe.w, pipe.C), device=device, dtype=torch.float32))
+                      torch.empty((0, 2, pipe.h, pipe.w, pipe.C), device=device, dtype=torch.float32))
         gathered = dvt_dist.collate_maps(local_maps, len(todo))       # the single exchange of the path (NCCL all-gather)
         if rank == 0:
-            print(f"Collated denoised maps of {gathered.shape[0]} images on every rank: {tuple(gathered.shape)}")
+            print(f"Collated raw + denoised maps of {gathered.shape[0]} images on every rank: {tuple(gathered.shape)}")
             if args.collate_out is not None:
-                torch.save({"denoised_feats": gathered.cpu(), "files": [f for _, f in todo], "model": args.model},
-                           args.collate_out)
+                torch.save({"raw_feats": gathered[:, 0].cpu(), "denoised_feats": gathered[:, 1].cpu(),
+                            "files": [f for _, f in todo], "model": args.model}, args.collate_out)
     torch.cuda.synchronize()
     print(f"Total time: {datetime.timedelta(seconds=int(time.time() - start))}")
     if world > 1:

@@ -42,8 +42,25 @@ def main():
             assert o.param_groups[0]["lr"] == v and o.param_groups[1]["lr"] == v * 0.5
             vals.append(v)
         sched.append({"lr": lr, "min_lr": min_lr, "warmup_iters": warm, "num_iters": n, "iterations": its, "values": vals})
+    # ---- stage 2: CosineScheduler (dvt/utils/misc.py:211-241) and the two samplers (dvt/dataset/sampler.py:7-45) ----
+    import itertools
+    stage2 = []
+    for base, final, total in [(2e-4 * (32 * 8 / 256) ** 0.5, 1e-6, 400), (3e-3, 1e-5, 30), (1e-3, 0.0, 7)]:
+        sc = ref.CosineScheduler(base_value=base, final_value=final, total_iters=total, warmup_iters=int(total * 0.15),
+                                 start_warmup_value=0)
+        stage2.append({"base_value": base, "final_value": final, "total_iters": total, "warmup_iters": int(total * 0.15),
+                       "values": [float(sc[i]) for i in range(total + 3)]})
+    spec2 = importlib.util.spec_from_file_location("ref_sampler", "/root/reference/dvt/dataset/sampler.py")
+    smp = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(smp)
+    samplers = {"infinite_n5_first12": list(itertools.islice(iter(smp.InfiniteSampler(range(5))), 12))}
+    for world in (2, 3):
+        for rank in range(world):
+            d = smp.DistributedInfiniteSampler(range(11), num_replicas=world, rank=rank)
+            samplers[f"distributed_n11_w{world}_r{rank}_first14"] = [int(i) for i in itertools.islice(iter(d), 14)]
+            samplers[f"distributed_n11_w{world}_r{rank}_len"] = len(d)
     out = os.path.join(HERE, "store_and_schedule.json")
-    json.dump({"paths": cases, "schedules": sched}, open(out, "w"), indent=1)
+    json.dump({"paths": cases, "schedules": sched, "stage2_schedules": stage2, "samplers": samplers}, open(out, "w"), indent=1)
     print("wrote", out)
 
 

@@ -135,3 +135,47 @@ def test_sampling_stream_is_the_references_rng_stream():
             np.random.randint(0, args.num_views + 1, args.num_vis_samples)
         assert got[i].dtype == np.int32 and np.array_equal(got[i], ref)
     assert np.array_equal(tail, np.random.randint(0, 1 << 30, 4))
+
+
+def test_stage2_schedule_and_samplers_match_reference():
+    """Stage-2 host logic against goldens minted from the reference's own CosineScheduler (dvt/utils/misc.py:211-241) and
+    samplers (dvt/dataset/sampler.py:7-45): learning rate per iteration (incl. past the end), index streams per rank."""
+    import itertools
+    from dvt import dataset
+    from dvt.utils import misc
+    from oracle import train as OT
+    for s in GOLD["stage2_schedules"]:
+        kw = dict(base_value=s["base_value"], final_value=s["final_value"], total_iters=s["total_iters"],
+                  warmup_iters=s["warmup_iters"], start_warmup_value=0)
+        for it, ref in enumerate(s["values"]):
+            assert abs(misc.cosine_schedule(it, **kw) - ref) <= 1e-18 + 1e-14 * abs(ref), (s["total_iters"], it)
+        assert np.allclose(OT.cosine_schedule(**kw), s["values"][:s["total_iters"]], rtol=1e-14, atol=0)
+    smp = GOLD["samplers"]
+    assert list(itertools.islice(iter(dataset.InfiniteSampler(range(5))), 12)) == smp["infinite_n5_first12"]
+    for world in (2, 3):
+        for rank in range(world):
+            d = dataset.DistributedInfiniteSampler(range(11), num_replicas=world, rank=rank)
+            assert [int(i) for i in itertools.islice(iter(d), 14)] == smp[f"distributed_n11_w{world}_r{rank}_first14"]
+            assert len(d) == smp[f"distributed_n11_w{world}_r{rank}_len"]
+
+
+def test_feature_store_dataset_reads_pairs_and_skips_missing(tmp_path):
+    from dvt.dataset import FeatureStoreDataset
+    from dvt.store import FeatureStoreWriter
+    from dvt.utils import misc
+    h, w, C = 3, 4, 8
+    data_root = str(tmp_path / "d") + "/"
+    model = "vit_small_patch14_dinov2.lvd142m"
+    args = Namespace(data_root=data_root, save_root=str(tmp_path / "f"), model=model)
+    wr = FeatureStoreWriter()
+    raw, den = torch.arange(h * w * C, dtype=torch.float32).reshape(h, w, C), torch.ones(1, h, w, C)
+    wr.submit(*misc.feature_paths(args, data_root + "a/x.jpg"), raw, den)
+    wr.close()
+    lst = tmp_path / "l.txt"
+    lst.write_text("a/x.jpg 3\na/missing.jpg 1\n")
+    ds = FeatureStoreDataset(data_root, str(lst), f"{args.save_root}/denoised_features/{model}/")
+    assert len(ds) == 2
+    for i in range(2):                                   # the missing image falls back to an existing one
+        item = ds[i]
+        assert np.array_equal(item["original_feats"], raw.numpy()) and item["denoised_feats"].shape == (h, w, C)
+        assert "image" not in item
