@@ -27,6 +27,7 @@ int fit_begin(Fit* f, const float* bank, const float* coords, size_t bank_rows, 
               double lr, double min_lr, int warmup_iters, int freeze_step, double weight_decay, double loss_scale,
               int validate, cudaStream_t caller);
 int fit_check(Fit* f);
+int fit_set_artifact_grid(Fit* f, const int* i0, const float* w0, const float* w1);
 int fit_run(Fit* f, int count, int use_graphs, cudaStream_t st, int impl);
 int fit_losses(Fit* f, float* dst_host, int num_iters);
 int fit_losses_async(Fit* f, float* dst, int num_iters, cudaStream_t caller);
@@ -78,8 +79,8 @@ int dvt_device_error(unsigned int* code_out) {
 long long dvt_launch_count(void) { return dvt::launch_count(); }
 
 int dvt_set_debug_impl(int impl) {
-  if (impl != 0 && impl != 1 && impl != -1) {
-    dvt::set_last_error("dvt_set_debug_impl: impl must be -1, 0 or 1");
+  if (impl != 0 && impl != 1 && impl != 2 && impl != -1) {
+    dvt::set_last_error("dvt_set_debug_impl: impl must be -1, 0, 1 or 2");
     return DVT_ERR_INVALID;
   }
   dvt::g_debug_impl_override = impl;
@@ -320,6 +321,10 @@ int dvt_fit_begin(dvt_fit_t* h, const float* bank_feats, const float* bank_coord
   DVT_REQUIRE(h, "dvt_fit_begin: null handle");
   return fit_begin(reinterpret_cast<Fit*>(h), bank_feats, bank_coords, bank_rows, idx_host, num_iters, lr, min_lr,
                    warmup_iters, freeze_step, weight_decay, loss_scale, validate, reinterpret_cast<cudaStream_t>(stream));
+}
+int dvt_fit_set_artifact_grid(dvt_fit_t* h, const int* i0_host, const float* w0_host, const float* w1_host) {
+  DVT_REQUIRE(h, "dvt_fit_set_artifact_grid: null handle");
+  return fit_set_artifact_grid(reinterpret_cast<Fit*>(h), i0_host, w0_host, w1_host);
 }
 int dvt_fit_check(dvt_fit_t* h) {
   DVT_REQUIRE(h, "dvt_fit_check: null handle");

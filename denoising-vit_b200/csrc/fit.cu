@@ -320,6 +320,15 @@ struct LossArgs {
   float* losses;            // [num_iters, 5]; this step's slots are used
   int n, C, hw;
   float loss_scale;
+  // F.grid_sample(G, coords, bilinear, align_corners=True) at the reference's linspace(-1, 1) node coordinates: in fp32
+  // a node's unnormalised position ((x + 1) / 2) * (size - 1) is not always the integer it stands for, so the sample
+  // reads (and its gradient reaches) a neighbouring cell with a weight of ~1e-6.  Adam normalises gradients, so that
+  // leakage decides the update of cells that were not sampled themselves.  Per axis node: first cell, weight of that cell,
+  // weight of the next one (oracle/fit.py::artifact_axis_table; nullptr: plain cell indexing).
+  const int* ax_i0;         // [gw] x nodes then [gh] y nodes
+  const float* ax_w0;
+  const float* ax_w1;
+  int gw, gh;
 };
 
 // NV = float4 per lane (ceil(C / 128)); all global loads of a row are issued before the first use.
@@ -334,11 +343,26 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
   const int C = a.C, nvec = row_ok ? (a.C >> 2) : 0;  // a warp without a row loads / stores nothing
   const int br = a.sr.rows(a.n)[row];
   float* losses = a.losses + (size_t)a.sr.step() * 5;
-  const int cell = br % a.hw;  // exact (r, c) of the patch inside its view: the "shared artifact coordinate"
+  const int cell = br % a.hw;  // (r, c) of the patch inside its view: the "shared artifact coordinate"
+  // the (up to four) cells grid_sample touches for this node and their bilinear weights (warp-uniform; weight 0 = unused;
+  // statically indexed so that they stay in registers)
+  int cidx[4] = {cell, cell, cell, cell};
+  float cw[4] = {1.f, 0.f, 0.f, 0.f};
+  if (a.ax_i0) {
+    const int cy = cell / a.gw, cx = cell - cy * a.gw;
+    const int x0 = a.ax_i0[cx], y0 = a.ax_i0[a.gw + cy];
+    const float wx0 = a.ax_w0[cx], wx1 = a.ax_w1[cx], wy0 = a.ax_w0[a.gw + cy], wy1 = a.ax_w1[a.gw + cy];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // nw, ne, sw, se like ATen's grid_sampler_2d
+      const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+      const bool inside = xx >= 0 && xx < a.gw && yy >= 0 && yy < a.gh;   // zero padding outside the map
+      cidx[k] = inside ? yy * a.gw + xx : cell;
+      cw[k] = inside ? ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0) : 0.f;
+    }
+  }
   const float4* raw4 = reinterpret_cast<const float4*>(a.raw + (size_t)row * a.ld_raw);
   const float4* raw4lo = reinterpret_cast<const float4*>(a.raw + a.raw_plane + (size_t)row * a.ld_raw);
   const float4* F4 = reinterpret_cast<const float4*>(a.F + (size_t)row * C);
-  const float4* G4 = reinterpret_cast<const float4*>(a.G + (size_t)cell * C);
   const float4* R4 = HAS_R ? reinterpret_cast<const float4*>(a.R + (size_t)row * C) : nullptr;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 pred[NV], raw[NV], rp[HAS_R ? NV : 1];
@@ -349,7 +373,14 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       const int v = lane + 32 * i;
       const bool ok = v < nvec;
       f[i] = ok ? F4[v] : z4;
-      gg[i] = ok ? __ldg(G4 + v) : z4;
+      gg[i] = z4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (cw[k] != 0.f) {   // warp-uniform; one corner with weight 1 unless the node leaks into its neighbours
+          const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(a.G + (size_t)cidx[k] * C) + v) : z4;
+          gg[i].x += t.x * cw[k]; gg[i].y += t.y * cw[k]; gg[i].z += t.z * cw[k]; gg[i].w += t.w * cw[k];
+        }
+      }
       raw[i] = ok ? raw4[v] : z4;
       rl[i] = ok ? raw4lo[v] : z4;
       if (HAS_R) rp[i] = ok ? R4[v] : z4;
@@ -403,9 +434,16 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       *reinterpret_cast<float4*>(dp + a.plane) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
     }
     if (a.gG) {
-      float* dst = a.gG + (size_t)cell * C + v * 4;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
-                   : "memory");
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // one cell with weight 1 unless the node leaks into its neighbours
+        if (cw[k] != 0.f) {
+          float* dst = a.gG + (size_t)cidx[k] * C + v * 4;
+          const float wk = cw[k];
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x * wk), "f"(d.y * wk), "f"(d.z * wk),
+                       "f"(d.w * wk)
+                       : "memory");
+        }
+      }
     }
     if (HAS_R) {
       // gt_residual = raw - denoised - shared = raw - (pred - R); e = R - gt = pred - raw
@@ -770,6 +808,8 @@ struct Fit {
   cudaEvent_t ev_upload[2] = {};               // H2D of slot s complete
   cudaEvent_t ev_run_done[2] = {};             // last fit_run that read slot s complete
   bool run_done_valid[2] = {false, false};
+  int* ax_i0 = nullptr;                        // grid_sample node tables of the artifact map (fit_set_artifact_grid), or null
+  float *ax_w0 = nullptr, *ax_w1 = nullptr;
   int* flags_dev = nullptr;                    // bit 0: a coordinate outside [0, 1]; bit 1: a sampled row out of range
   int* flags_pinned = nullptr;
   double sched_key[6] = {-1, -1, -1, -1, -1, -1};  // (num_iters, warmup, lr, min_lr, freeze_step) of the uploaded tables
@@ -1030,6 +1070,26 @@ int fit_get_param(Fit* f, const char* name_c, float* dst, size_t numel) {
   } else {
     DVT_CUDA_OK(cudaMemcpy(dst, f->sp + s->off, numel * 4, cudaMemcpyDefault));
   }
+  return DVT_OK;
+}
+
+// Installs the per-node tables of F.grid_sample(G, linspace(-1, 1) nodes, align_corners=True) (see LossArgs): HOST arrays
+// of gw + gh entries (x nodes first).  The caller computes them with the reference's own fp32 arithmetic
+// (dvt/fit.py::artifact_axis_table).  Changes the step kernels' arguments: captured graphs are dropped.
+int fit_set_artifact_grid(Fit* f, const int* i0, const float* w0, const float* w1) {
+  DVT_REQUIRE(i0 && w0 && w1, "fit_set_artifact_grid: null argument");
+  const size_t n = (size_t)f->gw + f->gh;
+  DVT_CUDA_OK(cudaDeviceSynchronize());
+  fit_drop_graphs(f);
+  if (!f->ax_i0) {
+    int rc = fit_alloc(f, (void**)&f->ax_i0, n * 4);
+    if (!rc) rc = fit_alloc(f, (void**)&f->ax_w0, n * 4);
+    if (!rc) rc = fit_alloc(f, (void**)&f->ax_w1, n * 4);
+    if (rc) return rc;
+  }
+  DVT_CUDA_OK(cudaMemcpy(f->ax_i0, i0, n * 4, cudaMemcpyHostToDevice));
+  DVT_CUDA_OK(cudaMemcpy(f->ax_w0, w0, n * 4, cudaMemcpyHostToDevice));
+  DVT_CUDA_OK(cudaMemcpy(f->ax_w1, w1, n * 4, cudaMemcpyHostToDevice));
   return DVT_OK;
 }
 
@@ -1391,6 +1451,7 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   la.raw = f->rawb; la.ld_raw = f->ld_raw; la.raw_plane = p_raw; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
   la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.plane = p_nc; la.gG = phase2 ? nullptr : sg + f->G.off;
   la.losses = f->losses; la.n = n; la.C = C; la.hw = f->hw; la.loss_scale = f->loss_scale;
+  la.ax_i0 = f->ax_i0; la.ax_w0 = f->ax_w0; la.ax_w1 = f->ax_w1; la.gw = f->gw; la.gh = f->gh;
   FIT_RC(launch_loss(la, st, pdl));
   // ---- backward ----
   FIT_RC(fork(sB, f->ev[2]));

@@ -62,6 +62,120 @@ __device__ __forceinline__ void epi_scalar_tail(const GemmEpi& e, const GemmShap
   }
 }
 
+// One 32-row x 32-column chunk of an accumulator tile, as read by tcgen05.ld 32x32b (thread = row): transpose through the
+// warp's shared-memory scratch, then the fused epilogue in the coalesced layout (each lane: 4 consecutive columns of 8
+// rows).  m0: global row of this lane's first row (tile row base + quadrant * 32 + lane / 8); n_base: global column of the
+// chunk.  Shared by the single-CTA and the CTA-pair kernels.
+__device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, float* scr, int lane, const uint32_t (&r)[32],
+                                          int n_base, int m0, bool has_k) {
+  // ---- transpose through smem: afterwards each lane holds 4 consecutive columns of 8 rows.  No math on the
+  // thread-per-row registers: everything that depends on the column (bias, LayerScale, ...) is loaded once per
+  // chunk as a float4 in the coalesced layout below.
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(scr + lane * SCR_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  __syncwarp();
+  const int col4 = (lane & 7) * 4;
+  const int n = n_base + col4;
+  if (n + 3 < s.N) {
+    // ---------------- vector path ----------------
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (e.out_mode == OUT_F32_RESID && e.gamma) g4 = __ldg(reinterpret_cast<const float4*>(e.gamma + n));
+    float4 xin[8];
+    if (e.out_mode == OUT_F32_RESID) {  // issue all residual loads before any store (memory-level parallelism)
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int m = m0 + 4 * jj;
+        if (m < s.M) xin[jj] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) + (size_t)m * e.ldo + n);
+      }
+    }
+    const bool plain = e.mask == nullptr && e.mask_f32 == nullptr && e.alpha == 1.0f && has_k;
+    if (plain && e.out_mode == OUT_BF16) {
+      // ---- fast path: bias (+ GELU / ReLU) -> bf16.  The activation is chosen ONCE per chunk, the row loop is
+      // branch-free (QKV and fc1+GELU, the two largest epilogues of the ViT forward).
+      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
+      if (e.act == ACT_GELU) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int m = m0 + 4 * jj;
+          float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+          uint2 pk;
+          pk.x = pack_bf16x2(gelu_erf(x.x + b4.x), gelu_erf(x.y + b4.y));
+          pk.y = pack_bf16x2(gelu_erf(x.z + b4.z), gelu_erf(x.w + b4.w));
+          if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
+        }
+      } else {
+        const float lo = e.act == ACT_RELU ? 0.0f : -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int m = m0 + 4 * jj;
+          float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+          uint2 pk;
+          pk.x = pack_bf16x2(fmaxf(x.x + b4.x, lo), fmaxf(x.y + b4.y, lo));
+          pk.y = pack_bf16x2(fmaxf(x.z + b4.z, lo), fmaxf(x.w + b4.w, lo));
+          if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
+        }
+      }
+    } else if (plain && e.out_mode == OUT_F32_RESID && e.act == ACT_NONE) {
+      // ---- fast path: x += gamma * (acc + bias)  (attention out-proj, fc2) ----
+      float* outp = reinterpret_cast<float*>(e.out);
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int m = m0 + 4 * jj;
+        const float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+        float4 o = xin[jj];
+        o.x = fmaf(g4.x, x.x + b4.x, o.x); o.y = fmaf(g4.y, x.y + b4.y, o.y);
+        o.z = fmaf(g4.z, x.z + b4.z, o.z); o.w = fmaf(g4.w, x.w + b4.w, o.w);
+        if (m < s.M) *reinterpret_cast<float4*>(outp + (size_t)m * e.ldo + n) = o;
+      }
+    } else {
+      // ---- generic path (fit epilogues: masks, split planes, atomics, remap) ----
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+      const int i = (lane >> 3) + 4 * jj;
+      const int m = m0 + 4 * jj;
+      float4 x = *reinterpret_cast<const float4*>(scr + i * SCR_PITCH + col4);
+      if (m >= s.M) continue;
+      if (!has_k) x = make_float4(0.f, 0.f, 0.f, 0.f);
+      x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+      if (e.act == ACT_GELU) {
+        x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+      } else if (e.act == ACT_RELU) {
+        x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+      }
+      if (e.mask_f32) {
+        const float4 h = *reinterpret_cast<const float4*>(e.mask_f32 + (size_t)m * e.ldmask + n);
+        x.x = h.x > 0.f ? x.x : 0.f; x.y = h.y > 0.f ? x.y : 0.f; x.z = h.z > 0.f ? x.z : 0.f; x.w = h.w > 0.f ? x.w : 0.f;
+      } else if (e.mask) {
+        const uint2 hb = *reinterpret_cast<const uint2*>(e.mask + (size_t)m * e.ldmask + n);
+        const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
+        const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
+        if (e.mask_mode == 1) {  // GELU backward: the mask tensor is the forward pre-activation
+          x.x *= gelu_grad(__low2float(h01)); x.y *= gelu_grad(__high2float(h01));
+          x.z *= gelu_grad(__low2float(h23)); x.w *= gelu_grad(__high2float(h23));
+        } else {
+          x.x = __low2float(h01) > 0.f ? x.x : 0.f; x.y = __high2float(h01) > 0.f ? x.y : 0.f;
+          x.z = __low2float(h23) > 0.f ? x.z : 0.f; x.w = __high2float(h23) > 0.f ? x.w : 0.f;
+        }
+      }
+      if (e.alpha != 1.0f) { x.x *= e.alpha; x.y *= e.alpha; x.z *= e.alpha; x.w *= e.alpha; }
+      if (e.out_mode == OUT_F32_RESID) {
+        float4 o = xin[jj];
+        o.x = fmaf(g4.x, x.x, o.x); o.y = fmaf(g4.y, x.y, o.y); o.z = fmaf(g4.z, x.z, o.z); o.w = fmaf(g4.w, x.w, o.w);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n) = o;
+      } else {
+        epi_post4(e, m, n, x);
+      }
+    }
+    }
+  } else {
+    // ---------------- ragged N tail: scalar path ----------------
+    epi_scalar_tail(e, s, scr, lane, m0, n, has_k);
+  }
+  }
+
 template <int BN, int STAGES, bool TF32, bool A_MN, bool B_MN, bool X3 = false>
 __global__ void __launch_bounds__(GemmSmem<BN, STAGES, X3>::THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmShape s,
@@ -290,113 +404,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         const int n_base = tn * BN + c * 32;
         if (n_base >= s.N) continue;  // whole chunk out of range (warp-uniform)
-        // ---- transpose through smem: afterwards each lane holds 4 consecutive columns of 8 rows.  No math on the
-        // thread-per-row registers: everything that depends on the column (bias, LayerScale, ...) is loaded once per
-        // chunk as a float4 in the coalesced layout below.
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(scr + lane * SCR_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        const int col4 = (lane & 7) * 4;
-        const int n = n_base + col4;
-        const int m0 = tm * BM + quad * 32 + (lane >> 3);
-        if (n + 3 < s.N) {
-          // ---------------- vector path ----------------
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (e.out_mode == OUT_F32_RESID && e.gamma) g4 = __ldg(reinterpret_cast<const float4*>(e.gamma + n));
-          float4 xin[8];
-          if (e.out_mode == OUT_F32_RESID) {  // issue all residual loads before any store (memory-level parallelism)
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int m = m0 + 4 * jj;
-              if (m < s.M) xin[jj] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) + (size_t)m * e.ldo + n);
-            }
-          }
-          const bool plain = e.mask == nullptr && e.mask_f32 == nullptr && e.alpha == 1.0f && has_k;
-          if (plain && e.out_mode == OUT_BF16) {
-            // ---- fast path: bias (+ GELU / ReLU) -> bf16.  The activation is chosen ONCE per chunk, the row loop is
-            // branch-free (QKV and fc1+GELU, the two largest epilogues of the ViT forward).
-            __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
-            if (e.act == ACT_GELU) {
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const int m = m0 + 4 * jj;
-                float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
-                uint2 pk;
-                pk.x = pack_bf16x2(gelu_erf(x.x + b4.x), gelu_erf(x.y + b4.y));
-                pk.y = pack_bf16x2(gelu_erf(x.z + b4.z), gelu_erf(x.w + b4.w));
-                if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
-              }
-            } else {
-              const float lo = e.act == ACT_RELU ? 0.0f : -INFINITY;
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const int m = m0 + 4 * jj;
-                float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
-                uint2 pk;
-                pk.x = pack_bf16x2(fmaxf(x.x + b4.x, lo), fmaxf(x.y + b4.y, lo));
-                pk.y = pack_bf16x2(fmaxf(x.z + b4.z, lo), fmaxf(x.w + b4.w, lo));
-                if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
-              }
-            }
-          } else if (plain && e.out_mode == OUT_F32_RESID && e.act == ACT_NONE) {
-            // ---- fast path: x += gamma * (acc + bias)  (attention out-proj, fc2) ----
-            float* outp = reinterpret_cast<float*>(e.out);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int m = m0 + 4 * jj;
-              const float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
-              float4 o = xin[jj];
-              o.x = fmaf(g4.x, x.x + b4.x, o.x); o.y = fmaf(g4.y, x.y + b4.y, o.y);
-              o.z = fmaf(g4.z, x.z + b4.z, o.z); o.w = fmaf(g4.w, x.w + b4.w, o.w);
-              if (m < s.M) *reinterpret_cast<float4*>(outp + (size_t)m * e.ldo + n) = o;
-            }
-          } else {
-            // ---- generic path (fit epilogues: masks, split planes, atomics, remap) ----
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-            const int i = (lane >> 3) + 4 * jj;
-            const int m = m0 + 4 * jj;
-            float4 x = *reinterpret_cast<const float4*>(scr + i * SCR_PITCH + col4);
-            if (m >= s.M) continue;
-            if (!has_k) x = make_float4(0.f, 0.f, 0.f, 0.f);
-            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-            if (e.act == ACT_GELU) {
-              x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
-            } else if (e.act == ACT_RELU) {
-              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-            }
-            if (e.mask_f32) {
-              const float4 h = *reinterpret_cast<const float4*>(e.mask_f32 + (size_t)m * e.ldmask + n);
-              x.x = h.x > 0.f ? x.x : 0.f; x.y = h.y > 0.f ? x.y : 0.f; x.z = h.z > 0.f ? x.z : 0.f; x.w = h.w > 0.f ? x.w : 0.f;
-            } else if (e.mask) {
-              const uint2 hb = *reinterpret_cast<const uint2*>(e.mask + (size_t)m * e.ldmask + n);
-              const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
-              const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
-              if (e.mask_mode == 1) {  // GELU backward: the mask tensor is the forward pre-activation
-                x.x *= gelu_grad(__low2float(h01)); x.y *= gelu_grad(__high2float(h01));
-                x.z *= gelu_grad(__low2float(h23)); x.w *= gelu_grad(__high2float(h23));
-              } else {
-                x.x = __low2float(h01) > 0.f ? x.x : 0.f; x.y = __high2float(h01) > 0.f ? x.y : 0.f;
-                x.z = __low2float(h23) > 0.f ? x.z : 0.f; x.w = __high2float(h23) > 0.f ? x.w : 0.f;
-              }
-            }
-            if (e.alpha != 1.0f) { x.x *= e.alpha; x.y *= e.alpha; x.z *= e.alpha; x.w *= e.alpha; }
-            if (e.out_mode == OUT_F32_RESID) {
-              float4 o = xin[jj];
-              o.x = fmaf(g4.x, x.x, o.x); o.y = fmaf(g4.y, x.y, o.y); o.z = fmaf(g4.z, x.z, o.z); o.w = fmaf(g4.w, x.w, o.w);
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n) = o;
-            } else {
-              epi_post4(e, m, n, x);
-            }
-          }
-          }
-        } else {
-          // ---------------- ragged N tail: scalar path ----------------
-          epi_scalar_tail(e, s, scr, lane, m0, n, has_k);
-        }
+        epi_chunk(e, s, scr, lane, r, n_base, tm * BM + quad * 32 + (lane >> 3), has_k);
         __syncwarp();
         if (ew == 0 && lane == 0) stampt(8 + (c & 7));  // chunk done (profiling aid)
       }
@@ -578,6 +586,9 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
               "gemm: operands must be 16-byte aligned");
   // wide tiles when N is large enough to fill them; narrow ones for the small fit GEMMs
   const bool wide = s.N >= 256 && (s.N % 256 == 0 || s.N > 1024);
+  if (dtype == TMAP_BF16 && !s.a_mn && !s.b_mn && wide && s.splits == 1 && s.M >= 256 && epi.out_mode != OUT_F32_ATOMIC &&
+      impl != GEMM_TCGEN05_1CTA && gemm_cg2_enabled())
+    return launch_gemm_cg2(A, lda, B, ldb, s, epi, stream);  // 256 x 256 tiles on CTA pairs (tcgen05 cta_group::2)
   CUtensorMap tmA, tmB;
   int rc;
   if (s.a_mn) rc = make_tmap_2d(&tmA, A, dtype, (uint64_t)s.K, (uint64_t)s.M, (uint64_t)lda * elem, bk, 64);

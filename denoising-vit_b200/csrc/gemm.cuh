@@ -159,12 +159,17 @@ __device__ __forceinline__ void epi_post4(const GemmEpi& e, int m, int n, float4
   }
 }
 
-enum GemmImpl { GEMM_TCGEN05 = 0, GEMM_SIMT_DEBUG = 1 };
+enum GemmImpl { GEMM_TCGEN05 = 0, GEMM_SIMT_DEBUG = 1, GEMM_TCGEN05_1CTA = 2 /* tcgen05, never the CTA-pair kernel */ };
 
 // dtype: TMAP_BF16 (kind::f16, bf16 operands) or TMAP_F32 (kind::tf32, fp32 operands; K-major only).
 // lda / ldb: row pitch in elements of the stored matrix ([M,K] / [N,K], or [K,M] / [K,N] for MN-major operands).
 int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dtype, const GemmShape& shape,
                    const GemmEpi& epi, cudaStream_t stream, int impl = -1 /* -1: process default */);
+
+// CTA-pair kernel (gemm2.cu): bf16, K-major operands, no split-K; launch_gemm_tn routes the large GEMMs there
+// (DVT_GEMM_CG2=0 keeps everything on the single-CTA kernels).
+int launch_gemm_cg2(const void* A, int lda, const void* B, int ldb, const GemmShape& s, const GemmEpi& e, cudaStream_t stream);
+bool gemm_cg2_enabled();
 
 int default_gemm_impl();
 int gemm_prepare();

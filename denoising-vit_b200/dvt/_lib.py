@@ -58,6 +58,7 @@ SIGNATURES = {
     "dvt_fit_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),
     "dvt_fit_init_params": (c_int, [c_void_p, ctypes.c_ulonglong, c_void_p]),
     "dvt_fit_check": (c_int, [c_void_p]),
+    "dvt_fit_set_artifact_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dvt_fit_losses_async": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "dvt_fit_get_param": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
     "dvt_fit_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_double, c_double, c_int, c_int,

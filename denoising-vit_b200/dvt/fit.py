@@ -35,13 +35,36 @@ def _get(module, path):
     return obj
 
 
+def artifact_axis_table(size: int):
+    """What `F.grid_sample(G, coords, bilinear, align_corners=True)` does with the reference's node coordinates
+    `torch.linspace(-1, 1, size)` (main_img_denoising.py:21-25,58-62) along one axis, in the same fp32 arithmetic as ATen
+    (`grid_sampler_unnormalize`: ((x + 1) / 2) * (size - 1); corner weights (i0 + 1) - ix and ix - i0): per node the first
+    cell it touches and the weights of that cell and of the next one.  For 37 nodes, 9 are not exact integers in fp32 and
+    leak ~1e-6 of their value / gradient into a neighbour."""
+    x = torch.linspace(-1, 1, size, dtype=torch.float32)
+    ix = ((x + 1.0) / 2) * (size - 1)
+    i0 = torch.floor(ix)
+    w1 = ix - i0
+    w0 = (i0 + 1) - ix
+    return i0.to(torch.int32), w0, w1
+
+
 class FitEngine:
-    def __init__(self, feat_dim: int, noise_map_height: int, noise_map_width: int, pixel_bsz: int, meta: HashGridMeta):
+    def __init__(self, feat_dim: int, noise_map_height: int, noise_map_width: int, pixel_bsz: int, meta: HashGridMeta,
+                 exact_grid_sample: bool = True):
         self.C, self.h, self.w, self.bsz, self.meta = feat_dim, noise_map_height, noise_map_width, pixel_bsz, meta
         h = c_void_p()
         check(lib().dvt_fit_create(byref(h), feat_dim, noise_map_height, noise_map_width, pixel_bsz, *meta.c_args()),
               "dvt_fit_create")
         self._h = h
+        if exact_grid_sample:   # reproduce grid_sample's fp32 behaviour at the node coordinates (see artifact_axis_table)
+            xi, xw0, xw1 = artifact_axis_table(noise_map_width)
+            yi, yw0, yw1 = artifact_axis_table(noise_map_height)
+            i0 = np.ascontiguousarray(torch.cat([xi, yi]).numpy())
+            w0 = np.ascontiguousarray(torch.cat([xw0, yw0]).numpy())
+            w1 = np.ascontiguousarray(torch.cat([xw1, yw1]).numpy())
+            check(lib().dvt_fit_set_artifact_grid(self._h, i0.ctypes.data_as(c_void_p), w0.ctypes.data_as(c_void_p),
+                                                  w1.ctypes.data_as(c_void_p)), "dvt_fit_set_artifact_grid")
         self.num_iters = 0
         self._keep = None
 

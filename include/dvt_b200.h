@@ -46,7 +46,8 @@ long long dvt_launch_count(void);
  * milestones of CTA 0: entry, setup done, first operands landed, MMAs issued, epilogue start, epilogue end, exit. */
 int dvt_debug_set_timestamp_buffer(unsigned long long* dev_buf16);
 /* Process-wide kernel implementation switch for debugging: 0 = tcgen05 tensor-core kernels (default),
- * 1 = plain SIMT reference kernels (same semantics, slow).  Also settable with DVT_GEMM_IMPL=simt. */
+ * 1 = plain SIMT reference kernels (same semantics, slow; also settable with DVT_GEMM_IMPL=simt), 2 = tcgen05 without the
+ * CTA-pair GEMM (cta_group::2; DVT_GEMM_CG2=0 does the same for a whole process), -1 = back to the default. */
 int dvt_set_debug_impl(int impl);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -176,6 +177,13 @@ int dvt_fit_init_params(dvt_fit_t* h, unsigned long long seed, void* stream);
 int dvt_fit_begin(dvt_fit_t* h, const float* bank_feats, const float* bank_coords, size_t bank_rows,
                   const int32_t* idx_host, int num_iters, double lr, double min_lr, int warmup_iters, int freeze_step,
                   double weight_decay, double loss_scale, int validate, void* stream);
+/* How the shared artifact map G is sampled at the reference's node coordinates (offline_denoiser.py:92-101:
+ * F.grid_sample(G, linspace(-1, 1) nodes, bilinear, align_corners=True)).  In fp32 a node's unnormalised position is not
+ * always the integer it stands for, so the reference reads -- and sends gradient to -- a neighbouring cell with a weight
+ * of ~1e-6; Adam normalises gradients, so this decides the update of cells that were not sampled themselves.  HOST
+ * tables of gw + gh entries (x nodes first): first cell, weight of that cell, weight of the next cell, computed by the
+ * caller with the reference's own fp32 arithmetic.  Without this call rows are attributed to their cell with weight 1. */
+int dvt_fit_set_artifact_grid(dvt_fit_t* h, const int* i0_host, const float* w0_host, const float* w1_host);
 /* Reports (and clears) the input-validation result of the fits begun since the last check.  Blocks. */
 int dvt_fit_check(dvt_fit_t* h);
 /* Runs the next `count` optimisation steps.  graph_steps > 0: CUDA graphs of that many steps. */

@@ -106,3 +106,39 @@ def test_gemm_splitk_and_residual(impl):
     finally:
         L.check(L.lib().dvt_set_debug_impl(-1))
     assert L.device_error() == 0
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (257, 512, 128), (511, 1100, 200), (2740, 2304, 768), (43840, 768, 3072),
+                                   (1000, 3072, 768), (21904, 2304, 768)])
+def test_gemm_cta_pair_kernel(shape):
+    """The cta_group::2 kernel (256 x 256 tiles on CTA pairs, gemm2.cu) against torch and against the single-CTA tcgen05
+    kernel: same k-order of fp32 accumulation, so the two tensor-core paths must agree BIT for bit; ragged M (one CTA of
+    the pair without rows), ragged N > 1024, K tails, and every fused epilogue the ViT uses."""
+    from dvt import ops
+    L = _lib()
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gam = torch.rand(N, device="cuda", generator=g) + 0.5
+    x0 = torch.randn(M, N, device="cuda", generator=g)
+    outs = {}
+    for impl in (0, 2):       # 0: default (pair kernel for these shapes), 2: single-CTA kernel only
+        L.check(L.lib().dvt_set_debug_impl(impl))
+        try:
+            y32 = ops.gemm_tn(a, w, bias, None, out_dtype=torch.float32)
+            yg = ops.gemm_tn(a, w, bias, "gelu", out_dtype=torch.bfloat16)
+            x = x0.clone()
+            ops.gemm_tn_residual_(x, a, w, bias, gam)
+            torch.cuda.synchronize()
+        finally:
+            L.check(L.lib().dvt_set_debug_impl(-1))
+        outs[impl] = (y32, yg, x)
+    assert L.device_error() == 0
+    ref = a.float() @ w.float().t() + bias
+    assert (outs[0][0] - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert (outs[0][1].float() - torch.nn.functional.gelu(ref)).abs().max().item() < 3e-2
+    assert (outs[0][2] - (x0 + gam * ref)).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
+    for k in range(3):
+        assert torch.equal(outs[0][k], outs[2][k]), f"pair kernel differs from the single-CTA kernel (output {k})"

@@ -150,3 +150,54 @@ def test_module_forward_equals_oracle(phase2):
         den(raw, pc, neural_field=field)                      # 2-D call without artifact coordinates
     with pytest.raises(AssertionError):
         den(raw, pc, neural_field=field, shared_artifact_coords=gc, return_visualization=True)
+
+
+@pytest.mark.parametrize("h,w", [(37, 37), (16, 16), (5, 7)])
+def test_artifact_axis_table_reproduces_grid_sample(h, w):
+    """The per-node tables the CUDA loss kernel uses (dvt.fit.artifact_axis_table) reproduce ATen's
+    F.grid_sample(bilinear, align_corners=True) at the reference's linspace(-1, 1) nodes BIT for bit: the interpolated
+    value and the gradient every cell receives (for 37 x 37, 818 of the 1369 cells get a gradient != 1)."""
+    from dvt.fit import artifact_axis_table
+    C = 3
+    g = torch.Generator().manual_seed(0)
+    G = torch.randn(1, C, h, w, generator=g, requires_grad=True)
+    nodes = OF.make_patch_coordinates(h, w).reshape(-1, 2)
+    out = torch.nn.functional.grid_sample(G, nodes[None, None], mode="bilinear", align_corners=True)
+    out = out.squeeze(0).squeeze(1).t()                               # [h*w, C]
+    up = torch.randn(h * w, C, generator=g)
+    (out * up).sum().backward()
+    xi, xw0, xw1 = artifact_axis_table(w)
+    yi, yw0, yw1 = artifact_axis_table(h)
+    cells = G.detach()[0].permute(1, 2, 0).reshape(h * w, C)
+    val = torch.zeros(h * w, C)
+    grad = torch.zeros(h * w, C)
+    for r in range(h):
+        for c in range(w):
+            acc = torch.zeros(C)
+            for k in range(4):                                        # nw, ne, sw, se
+                xx, yy = int(xi[c]) + (k & 1), int(yi[r]) + (k >> 1)
+                wgt = (xw1[c] if k & 1 else xw0[c]) * (yw1[r] if k >> 1 else yw0[r])
+                if wgt != 0 and 0 <= xx < w and 0 <= yy < h:
+                    acc = acc + cells[yy * w + xx] * wgt
+                    grad[yy * w + xx] += up[r * w + c] * wgt
+            val[r * w + c] = acc
+    # values: the same four products; ATen's vectorised kernel may contract / order the sum differently (<= 1 ulp)
+    assert torch.allclose(val, out.detach(), rtol=0, atol=1e-6 * float(cells.abs().max()))
+    assert (val == out.detach()).float().mean().item() > 0.8
+    ref_grad = G.grad[0].permute(1, 2, 0).reshape(h * w, C)
+    assert torch.allclose(grad, ref_grad, rtol=0, atol=1e-6 * float(up.abs().max()))
+    # the SAME cells receive gradient: where grid_sample leaks into a neighbour, so do the tables (and nowhere else)
+    plain = torch.zeros(h * w, C)
+    plain += up                                                       # weight-1 attribution to the node's own cell
+    leak_ref, leak_tab = (ref_grad != plain), (grad != plain)
+    assert torch.equal(leak_ref.any(1), leak_tab.any(1))
+    if (h, w) == (37, 37):
+        ones = torch.zeros(h * w)
+        for r in range(h):
+            for c in range(w):
+                for k in range(4):
+                    xx, yy = int(xi[c]) + (k & 1), int(yi[r]) + (k >> 1)
+                    wgt = (xw1[c] if k & 1 else xw0[c]) * (yw1[r] if k >> 1 else yw0[r])
+                    if wgt != 0 and 0 <= xx < w and 0 <= yy < h:
+                        ones[yy * w + xx] += wgt
+        assert int((ones != 1).sum()) == 818

@@ -201,6 +201,11 @@ def test_training_run_matches_oracle():
     got_sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     for k, v in ref_sd.items():
         upd_ref, upd_got = v - sd[k], got_sd[k] - sd[k]
+        if k.endswith("attn.qkv.bias"):
+            # softmax is invariant to a shift of all keys: the exact gradient of the k-bias is zero, what Adam normalises
+            # there is rounding noise -- compare the q and v thirds only
+            keep = torch.cat([torch.arange(0, C), torch.arange(2 * C, 3 * C)])
+            upd_ref, upd_got = upd_ref[keep], upd_got[keep]
         assert _cos(upd_got, upd_ref) > 0.97, f"{k}: update cosine {_cos(upd_got, upd_ref)}"
     # optimiser state in torch.optim layout
     st = opt.state_dict()

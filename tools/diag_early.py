@@ -30,8 +30,9 @@ if __name__ == "__main__":
     ora = OF.fit(feats, coords, cfg["h"], cfg["w"], ometa, init, idx, lr=cfg["lr"], min_lr=cfg["min_lr"],
                  weight_decay=cfg["weight_decay"], warmup_iters=cfg["warmup_iters"], freeze_after=cfg["freeze_after"],
                  loss_scale=cfg["loss_scale"], log_every=1)
-    for tag, impl, env in (("tcgen05 3xTF32, sequential", 0, {"DVT_FIT_PIPELINE": "0"}), ("SIMT fp32, sequential", 1, {"DVT_FIT_PIPELINE": "0"}),
-                           ("tcgen05 3xTF32, pipelined", 0, {})):
+    prev = {}
+    for tag, impl, env in (("tcgen05 3xTF32, sequential", 0, {"DVT_FIT_PIPELINE": "0"}), ("tcgen05 3xTF32, sequential (again)", 0, {"DVT_FIT_PIPELINE": "0"}),
+                           ("SIMT fp32, sequential", 1, {"DVT_FIT_PIPELINE": "0"}), ("tcgen05 3xTF32, pipelined", 0, {})):
         os.environ.pop("DVT_FIT_PIPELINE", None)
         os.environ.update(env)
         feats, coords, init, idx, den, field, _ = T._setup(cfg)
@@ -51,8 +52,18 @@ if __name__ == "__main__":
             if ref.norm() == 0:
                 continue
             parts.append(f"{k} {float((got - ref).norm() / ref.norm()):.2e}")
+            if os.environ.get("DIAG_ELEMENTWISE") and k in ("G", "mlp.0.weight", "mlp.2.weight", "table"):
+                nz = ref.abs() > 0
+                rel = ((got - ref).abs()[nz] / ref.abs()[nz])
+                q = torch.quantile(rel[torch.randperm(rel.numel())[:2000000]].float(), torch.tensor([0.5, 0.9, 0.99, 0.999]))
+                parts.append(f"[{k} elementwise rel: median {q[0]:.1e} p90 {q[1]:.1e} p99 {q[2]:.1e} p99.9 {q[3]:.1e} "
+                             f"frac>1e-3 {float((rel > 1e-3).float().mean()):.2e} frac>0.5 {float((rel > 0.5).float().mean()):.2e}]")
             if k == "table":
                 touched = ref.abs() > 1.5 * ref.abs().median()
                 if touched.any():
                     parts.append(f"table(touched) {float((got - ref)[touched].norm() / ref[touched].norm()):.2e}")
         print(f"{tag:30s} T={steps} max rel loss dev {ldev:.2e} | " + "  ".join(parts), flush=True)
+        cur = {k: eng.get_param(k, init[k]).cpu().double() - init[k].double() for k in KEYS}
+        if prev:
+            print("      vs previous GPU run: " + "  ".join(f"{k} {float((cur[k] - prev[k]).norm() / (prev[k].norm() + 1e-30)):.2e}" for k in KEYS), flush=True)
+        prev = cur
