@@ -77,7 +77,7 @@ def kernel_rooflines(pipe, extract_bsz, dev):
     """The two kernels that dominate the step, each timed ALONE with CUDA events on the stream it is launched on
     (10 launches after 3 warm-ups, L2 flushed by a 256 MB write before every launch), through the library's unit entry
     points -- the same kernels, shapes and epilogues the timed region launches:
-      * gemm_tn_tc_kernel<256, 3> (bf16 tcgen05 GEMM): the four GEMMs of one ViT-B block at the extraction batch
+      * gemm_tn_cg2_kernel (bf16 tcgen05 GEMM on CTA pairs): the four GEMMs of one ViT-B block at the extraction batch
         (QKV, out-proj + LayerScale residual, fc1 + GELU, fc2 + LayerScale residual); algorithmic flops =
         SURVEY.md 8(d) per-view figures (4.85 + 1.62 + 12.93 GF) x views per launch set;
       * fit_adam_table_kernel (dense Adam sweep of the hash table): algorithmic bytes = 24 B x 19 741 760 parameters."""
@@ -352,7 +352,8 @@ def main():
             b.ls2.gamma.fill_(1.0)
     vit = vit.to(dev).eval()
     cfg = Stage1Config(num_iters=args.num_iters, warmup_iters=args.warmup_iters, n_levels=16, extract_bsz=args.extract_bsz,
-                       pixel_bsz=2048, graph_steps=args.graph_steps)
+                       pixel_bsz=2048, graph_steps=args.graph_steps,
+                       fit_engines=int(os.environ.get("DVT_FIT_ENGINES", Stage1Config.fit_engines)))
     pipe = Stage1Pipeline(vit, layer_index=11, input_size=(518, 518), cfg=cfg)
     h, w, C = pipe.h, pipe.w, pipe.C
 
@@ -465,8 +466,8 @@ def main():
         # kernel level (the contract).  Largest shares of the ncu launch list of this command
         # (profiles/*_launch_shares.txt): the dense Adam sweep, then the bf16 GEMM.
         gemm = {"bound": "tensor", "achieved": kr["gemm_tflops"], "peak": pk["bf16_tflops_burst"], "unit": "TFLOP/s",
-                    "frac": kr["gemm_tflops"] / pk["bf16_tflops_burst"], "traffic": ncu_traffic("gemm_tn_tc_kernel<256,3,bf16>"),
-                    "kernel": "gemm_tn_tc_kernel<256, 3> (bf16 tcgen05 GEMM, the 4 GEMMs of one ViT-B block)",
+                    "frac": kr["gemm_tflops"] / pk["bf16_tflops_burst"], "traffic": ncu_traffic("gemm_tn_cg2_kernel"),
+                    "kernel": "gemm_tn_cg2_kernel (bf16 tcgen05 cta_group::2 GEMM on CTA pairs, the 4 GEMMs of one ViT-B block)",
                     "algorithmic_flops_per_launch_set": kr["gemm_flops"], "ms_per_launch": kr["gemm_ms"],
                     "views_per_launch": args.extract_bsz, "timed": "alone, CUDA events, L2 flushed between launches",
                     "peak_source": pk["source"] + " (bf16 cuBLAS burst: kernel timed alone)"}

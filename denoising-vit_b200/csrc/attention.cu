@@ -320,26 +320,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mbar_arrive(s_empty);  // S_j lives in registers now: QK of tile j+1 may overwrite the TMEM buffer
         const int kbase = j * ATT_BK;
         const bool partial = kbase + ATT_BK > N;  // only the last tile can hold keys >= N
-        float m_tile = -INFINITY;
+        // eight independent maxima (a single running maximum is a chain of 128 dependent FMNMX: ~500 cycles of exposed
+        // latency per tile with only two softmax warps per scheduler)
+        float mx[8] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int nval = partial ? N - kbase - c * 32 : 32;  // valid keys in this chunk (warp-uniform)
           if (nval >= 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(sreg[c][i]));
+            for (int i = 0; i < 32; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(sreg[c][i]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (i < nval) m_tile = fmaxf(m_tile, __uint_as_float(sreg[c][i]));
+              if (i < nval) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(sreg[c][i]));
           }
         }
+        float m_tile = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
         m_tile *= scale_log2e;                      // scale > 0: max commutes with the scaling
         const float m_new = fmaxf(m_run, m_tile);  // finite: every tile has at least one valid key
         const bool grow = m_new - m_run > 8.0f;     // (first tile: m_run = -inf)
         const float m_use = grow ? m_new : m_run;
         const float alpha = grow ? ex2(m_run - m_new) : 1.0f;  // 0 on the first tile
         uint32_t packed[4][16];
-        float l_tile = 0.f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial row sums (same reason as the maxima)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int nval = partial ? N - kbase - c * 32 : 32;
@@ -350,7 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
               const float x1 = fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use);
               const float p0 = ex2(x0);
               const float p1 = (POLY && (i & 1)) ? ex2_fma(x1) : ex2(x1);
-              l_tile += p0 + p1;
+              ls[i & 3] += p0 + p1;
               packed[c][i] = pack_bf16x2(p0, p1);
             }
           } else {  // tail of the last key tile: keys >= N contribute neither to P nor to the row sum
@@ -359,11 +362,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
               float p0 = 0.f, p1 = 0.f;
               if (2 * i < nval) p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
               if (2 * i + 1 < nval) p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
-              l_tile += p0 + p1;
+              ls[i & 3] += p0 + p1;
               packed[c][i] = pack_bf16x2(p0, p1);
             }
           }
         }
+        const float l_tile = (ls[0] + ls[1]) + (ls[2] + ls[3]);
         if (j > 0) {
           // PV_{j-1} must have completed before the P buffer is overwritten / O is rescaled
           mbar_wait(&o_full[0], (j - 1) & 1, 18);

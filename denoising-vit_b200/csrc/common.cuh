@@ -94,6 +94,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// (A suspend-time hint on try_wait -- `mbarrier.try_wait ..., hint_ns` -- was measured in round 2: no effect on the attention
+// kernel, 0.365 -> 0.368 ms, and the fit's step chain got slower, so the plain form stays.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -321,18 +323,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): cheap enough for a GEMM epilogue.
+// erf with ONE transcendental: erfc(t) = 2^q(t) for t = |x|, q a degree-6 polynomial without constant term fitted to
+// log2(erfc(t)) on [0, 4.2] (weighted so that the absolute error of erf is minimised: max |err| 3.3e-7 in fp32, evaluated
+// against scipy.special.erf on 2e5 points); erf(x) = sign(x) (1 - 2^q).  t is clamped to 6 (erfc(6) = 2e-17 rounds 1 - e
+// to 1; the polynomial turns upward far outside its fitting range).  Round 1 used Abramowitz-Stegun 7.1.26 (a reciprocal
+// AND an exponential per element): in the fc1 + GELU epilogue the MUFU pipe -- 2 ops x 32 768 elements per tile -- cost
+// 2/3 of the tile's MMA time.
 __device__ __forceinline__ float fast_erf(float x) {
-  float ax = fabsf(x);
-  float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));  // MUFU.RCP, no IEEE fix-up sequence
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  float e = __expf(-ax * ax);
-  float r = fmaf(-p, e, 1.0f);
-  return copysignf(r, x);
+  const float t = fminf(fabsf(x), 6.0f);
+  float q = 1.580459628734477e-4f;
+  q = fmaf(q, t, -3.742739173536956e-3f);
+  q = fmaf(q, t, 3.1032528216293022e-2f);
+  q = fmaf(q, t, -1.498016394645605e-1f);
+  q = fmaf(q, t, -9.181337298819333e-1f);
+  q = fmaf(q, t, -1.6279281218285298f);
+  q *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return copysignf(1.0f - e, x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
 

@@ -333,7 +333,7 @@ struct LossArgs {
 
 // NV = float4 per lane (ceil(C / 128)); all global loads of a row are issued before the first use.
 template <int NV, bool HAS_R>
-__global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
+__global__ void __launch_bounds__(256, 2) fit_loss_kernel(LossArgs a) {
   pdl_wait();     // (no-ops unless launched with programmatic stream serialisation)
   pdl_trigger();
   const int row_raw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -344,21 +344,16 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
   const int br = a.sr.rows(a.n)[row];
   float* losses = a.losses + (size_t)a.sr.step() * 5;
   const int cell = br % a.hw;  // (r, c) of the patch inside its view: the "shared artifact coordinate"
-  // the (up to four) cells grid_sample touches for this node and their bilinear weights (warp-uniform; weight 0 = unused;
-  // statically indexed so that they stay in registers)
-  int cidx[4] = {cell, cell, cell, cell};
-  float cw[4] = {1.f, 0.f, 0.f, 0.f};
+  // the cell grid_sample reads for this node and its bilinear weight: per axis the heavier of the two corners (always
+  // inside the map).  The ~1e-6 share of the lighter corners is below one ulp of pred and is not read here; their share of
+  // the GRADIENT is what Adam amplifies, and fit_g_scatter_kernel delivers it.
+  int cmain = cell;
+  float wmain = 1.f;
   if (a.ax_i0) {
     const int cy = cell / a.gw, cx = cell - cy * a.gw;
-    const int x0 = a.ax_i0[cx], y0 = a.ax_i0[a.gw + cy];
-    const float wx0 = a.ax_w0[cx], wx1 = a.ax_w1[cx], wy0 = a.ax_w0[a.gw + cy], wy1 = a.ax_w1[a.gw + cy];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {  // nw, ne, sw, se like ATen's grid_sampler_2d
-      const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
-      const bool inside = xx >= 0 && xx < a.gw && yy >= 0 && yy < a.gh;   // zero padding outside the map
-      cidx[k] = inside ? yy * a.gw + xx : cell;
-      cw[k] = inside ? ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0) : 0.f;
-    }
+    const bool nx = a.ax_w1[cx] > a.ax_w0[cx], ny = a.ax_w1[a.gw + cy] > a.ax_w0[a.gw + cy];
+    cmain = (a.ax_i0[a.gw + cy] + (ny ? 1 : 0)) * a.gw + a.ax_i0[cx] + (nx ? 1 : 0);
+    wmain = (nx ? a.ax_w1[cx] : a.ax_w0[cx]) * (ny ? a.ax_w1[a.gw + cy] : a.ax_w0[a.gw + cy]);
   }
   const float4* raw4 = reinterpret_cast<const float4*>(a.raw + (size_t)row * a.ld_raw);
   const float4* raw4lo = reinterpret_cast<const float4*>(a.raw + a.raw_plane + (size_t)row * a.ld_raw);
@@ -373,13 +368,11 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       const int v = lane + 32 * i;
       const bool ok = v < nvec;
       f[i] = ok ? F4[v] : z4;
-      gg[i] = z4;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (cw[k] != 0.f) {   // warp-uniform; one corner with weight 1 unless the node leaks into its neighbours
-          const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(a.G + (size_t)cidx[k] * C) + v) : z4;
-          gg[i].x += t.x * cw[k]; gg[i].y += t.y * cw[k]; gg[i].z += t.z * cw[k]; gg[i].w += t.w * cw[k];
-        }
+      {  // the sampled value: the node's own cell times its corner weight.  (The ~1e-6 share of a neighbouring cell that
+         // grid_sample adds for 9 of 37 nodes changes pred by less than one fp32 ulp; reading it cost 5-10 us per step on
+         // the critical path.  The GRADIENT share of the neighbours is what Adam amplifies: fit_g_scatter_kernel keeps it.)
+        const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(a.G + (size_t)cmain * C) + v) : z4;
+        gg[i] = make_float4(t.x * wmain, t.y * wmain, t.z * wmain, t.w * wmain);
       }
       raw[i] = ok ? raw4[v] : z4;
       rl[i] = ok ? raw4lo[v] : z4;
@@ -433,18 +426,6 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
       *reinterpret_cast<float4*>(dp) = hi;
       *reinterpret_cast<float4*>(dp + a.plane) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
     }
-    if (a.gG) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {  // one cell with weight 1 unless the node leaks into its neighbours
-        if (cw[k] != 0.f) {
-          float* dst = a.gG + (size_t)cidx[k] * C + v * 4;
-          const float wk = cw[k];
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x * wk), "f"(d.y * wk), "f"(d.z * wk),
-                       "f"(d.w * wk)
-                       : "memory");
-        }
-      }
-    }
     if (HAS_R) {
       // gt_residual = raw - denoised - shared = raw - (pred - R); e = R - gt = pred - raw
       const float4 q = rp[i];
@@ -486,6 +467,59 @@ __global__ void __launch_bounds__(256) fit_loss_kernel(LossArgs a) {
     for (int k = 0; k < 8; ++k)
       if (k < nw) t += s_part[k][threadIdx.x];
     atomicAdd(losses + threadIdx.x, t);
+  }
+}
+
+// dG of phase 1, off the critical path: the loss kernel stores d pred (hi / lo planes); this kernel, on a side stream,
+// adds every row's d pred to the cells of G that F.grid_sample reads for the row's node (normally one cell with weight 1,
+// for 9 of 37 nodes per axis also a neighbour with a weight of ~1e-6: see LossArgs).  Only Adam(small) at the end of the
+// step consumes gG, so nothing on the main stream waits for these atomics.
+struct ScatterArgs {
+  const float* dpred;       // [2 planes][n, C]
+  size_t plane;
+  StepRows sr;
+  float* gG;                // [hw, C]
+  int n, C, hw, gw, gh;
+  const int* ax_i0;
+  const float* ax_w0;
+  const float* ax_w1;
+};
+__global__ void __launch_bounds__(256) fit_g_scatter_kernel(ScatterArgs a) {
+  pdl_wait();
+  pdl_trigger();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= a.n) return;
+  const int cell = a.sr.rows(a.n)[row] % a.hw;
+  int cidx[4] = {cell, cell, cell, cell};
+  float cw[4] = {1.f, 0.f, 0.f, 0.f};
+  if (a.ax_i0) {
+    const int cy = cell / a.gw, cx = cell - cy * a.gw;
+    const int x0 = a.ax_i0[cx], y0 = a.ax_i0[a.gw + cy];
+    const float wx0 = a.ax_w0[cx], wx1 = a.ax_w1[cx], wy0 = a.ax_w0[a.gw + cy], wy1 = a.ax_w1[a.gw + cy];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+      const bool inside = xx >= 0 && xx < a.gw && yy >= 0 && yy < a.gh;
+      cidx[k] = inside ? yy * a.gw + xx : cell;
+      cw[k] = inside ? ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0) : 0.f;
+    }
+  }
+  const float4* hi = reinterpret_cast<const float4*>(a.dpred + (size_t)row * a.C);
+  const float4* lo = reinterpret_cast<const float4*>(a.dpred + a.plane + (size_t)row * a.C);
+  for (int v = lane; v < (a.C >> 2); v += 32) {
+    const float4 h = hi[v], l = lo[v];
+    const float4 d = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);  // hi + lo == d pred exactly
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (cw[k] != 0.f) {
+        float* dst = a.gG + (size_t)cidx[k] * a.C + v * 4;
+        const float wk = cw[k];
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(d.x * wk), "f"(d.y * wk), "f"(d.z * wk),
+                     "f"(d.w * wk)
+                     : "memory");
+      }
+    }
   }
 }
 
@@ -783,6 +817,7 @@ struct Fit {
   int epoch_steps = 0;                         // pipelined steps enqueued since the sweeps were last joined
   bool enc_ready = false;                      // f->enc already holds the encoding of the next step
   int res_x3 = 1;                              // GEMM mode of the residual MLP: 1 = 3xTF32, 2 = plain TF32 (experiment)
+  int wgrad_x3 = 1;                            // GEMM mode of the field MLP's weight-gradient GEMMs (DVT_FIT_WGRAD_TF32=1: 2)
   bool pdl = true;                             // programmatic dependent launch along the kernel chains of a step
   bool pipe[2] = {true, true};                 // software-pipelined table sweep in phase 1 / 2 (see fit_enqueue_step)
   int sweep_ctas[2] = {0, 0};                  // persistent sweep CTAs in phase 1 / 2 (0 = many small CTAs)
@@ -890,6 +925,9 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
     //                               beside the chain: profiles/r2b_sweep_tma_experiment.txt; kept as a tested experiment)
     const char* tm = getenv("DVT_FIT_SWEEP_TMA");
     f->sweep_tma = tm && tm[0] == '1';
+    //   DVT_FIT_WGRAD_TF32=1        weight-gradient GEMMs of the field MLP in plain TF32 (experiment; not the default)
+    const char* wt = getenv("DVT_FIT_WGRAD_TF32");
+    f->wgrad_x3 = (wt && wt[0] == '1') ? 2 : 1;
     const char* rt = getenv("DVT_FIT_RES_TF32");
     f->res_x3 = (rt && rt[0] == '1') ? 2 : 1;
     const char* pd = getenv("DVT_FIT_PDL");
@@ -1449,7 +1487,8 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   // ---- loss + d pred ----
   LossArgs la;
   la.raw = f->rawb; la.ld_raw = f->ld_raw; la.raw_plane = p_raw; la.sr = sr; la.F = f->Fout; la.G = sp + f->G.off; la.R = phase2 ? f->Rout : nullptr;
-  la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.plane = p_nc; la.gG = phase2 ? nullptr : sg + f->G.off;
+  la.dpred = f->dpred; la.dR = phase2 ? f->dR : nullptr; la.plane = p_nc;
+  la.gG = nullptr;  // dG is scattered by fit_g_scatter_kernel on side C (phase 1), off the critical path
   la.losses = f->losses; la.n = n; la.C = C; la.hw = f->hw; la.loss_scale = f->loss_scale;
   la.ax_i0 = f->ax_i0; la.ax_w0 = f->ax_w0; la.ax_w1 = f->ax_w1; la.gw = f->gw; la.gh = f->gh;
   FIT_RC(launch_loss(la, st, pdl));
@@ -1459,11 +1498,22 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
     FIT_RC(fork(sC, f->ev[3]));
     FIT_RC(fork(sE, f->ev[11]));
   }
-  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl, pdl));          // side B
+  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl, pdl, f->wgrad_x3));          // side B
   FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl, pdl));  // main
   FIT_RC(fork(sB, f->ev[4]));  // dh1 ready
-  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl, pdl));           // side B (reads enc)
+  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl, pdl, f->wgrad_x3));           // side B (reads enc)
   FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl, pdl));
+  if (!phase2) {
+    // dG (+ grid_sample's neighbour shares) on side C, enqueued BEHIND the two data-gradient GEMMs: launched beside them, its
+    // 256 small CTAs take the registers the GEMM CTAs need and delay the critical path by ~10 us (measured, r2i)
+    FIT_RC(fork(sC, f->ev[3]));
+    ScatterArgs sa;
+    sa.dpred = f->dpred; sa.plane = p_nc; sa.sr = sr; sa.gG = sg + f->G.off; sa.n = n; sa.C = C; sa.hw = f->hw;
+    sa.gw = f->gw; sa.gh = f->gh; sa.ax_i0 = f->ax_i0; sa.ax_w0 = f->ax_w0; sa.ax_w1 = f->ax_w1;
+    DVT_CUDA_OK(launch_k(pdl, fit_g_scatter_kernel, dim3((n * 32 + tb - 1) / tb), dim3(tb), 0, sC, sa));
+    DVT_CUDA_OK(cudaGetLastError());
+    count_launch();
+  }
   // the gradient ring slot of this step was re-zeroed by the sweep of step t-2, which also produced the state the
   // next encode reads
   if (pipe && f->epoch_steps >= 2)
@@ -1482,9 +1532,9 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
     FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sE, impl, pdl, f->res_x3));
     DVT_CUDA_OK(cudaStreamWaitEvent(sE, f->ev[12], 0));
     FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sE, impl, pdl, f->res_x3));
-    FIT_RC(join(sC, f->ev[5]));
     FIT_RC(join(sE, f->ev[13]));
   }
+  FIT_RC(join(sC, f->ev[5]));
   FIT_RC(join(sB, f->ev[6]));  // all small-parameter gradients complete; enc no longer read by a wgrad
   // ---- Adam(small) on side B, beside the table work ----
   FIT_RC(fork(sB, f->ev[7]));

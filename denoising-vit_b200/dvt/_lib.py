@@ -6,7 +6,9 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_size_t, c_uint, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdvt_b200.so")
+# DVT_LIB_PATH: load another build of the library (A/B measurements of two source revisions on one GPU box; symbols the
+# other build lacks are skipped)
+LIB_PATH = os.environ.get("DVT_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libdvt_b200.so")
 
 
 class DvtError(RuntimeError):
@@ -88,6 +90,8 @@ def lib():
                 "(there is no CPU fallback)")
         l = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if not hasattr(l, name) and os.environ.get("DVT_LIB_PATH"):
+                continue
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args

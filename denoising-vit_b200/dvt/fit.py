@@ -57,7 +57,9 @@ class FitEngine:
         check(lib().dvt_fit_create(byref(h), feat_dim, noise_map_height, noise_map_width, pixel_bsz, *meta.c_args()),
               "dvt_fit_create")
         self._h = h
-        if exact_grid_sample:   # reproduce grid_sample's fp32 behaviour at the node coordinates (see artifact_axis_table)
+        import os
+        if exact_grid_sample and os.environ.get("DVT_FIT_EXACT_GRID", "1") != "0":
+            # reproduce grid_sample's fp32 behaviour at the node coordinates (see artifact_axis_table)
             xi, xw0, xw1 = artifact_axis_table(noise_map_width)
             yi, yw0, yw1 = artifact_axis_table(noise_map_height)
             i0 = np.ascontiguousarray(torch.cat([xi, yi]).numpy())

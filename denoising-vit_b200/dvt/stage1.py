@@ -29,6 +29,8 @@ class Stage1Config:
     loss_scale: float = 1024.0      # torch.amp.GradScaler("cuda", 2**10), never unscaled (main_img_denoising.py:55,88)
     graph_steps: int = 20
     log_losses: bool = False        # keep the per-step loss table of every image (out["losses"], pinned host memory)
+    fit_engines: int = 2            # fits kept in flight by run_images (one engine each): the step chain of a fit is a
+                                    # sequence of small latency-bound kernels, two independent chains fill each other's gaps
 
 
 class Stage1Pipeline:
@@ -42,21 +44,22 @@ class Stage1Pipeline:
         # module parameters live on the GPU: the per-image re-initialisation and the upload into the engine are then
         # device-side copies (the reference also builds its modules on the GPU, main_img_denoising.py:39-47)
         self.field = DVT.NeuralFeatureField(feat_dim=self.C, n_levels=cfg.n_levels).cuda()
-        self.engine = FitEngine(self.C, self.h, self.w, cfg.pixel_bsz, self.field.meta)
+        self.engines = [FitEngine(self.C, self.h, self.w, cfg.pixel_bsz, self.field.meta) for _ in range(max(1, cfg.fit_engines))]
+        self.engine = self.engines[0]
         self.base_seed = int(seed)               # parameter initialisation of image k uses (base_seed, k)
         self._image_counter = 0
         # coordinates of the final query (main_img_denoising.py:121-130), uploaded once: a pageable host-to-device copy
         # after the fit would block the host until the fit has finished and serialise run_images
         self._full_coords = make_patch_coordinates(self.h, self.w, 0, 1).to("cuda")
         assert self._full_coords.min() >= 0 and self._full_coords.max() <= 1
-        self._banks = [None, None]              # double-buffered feature banks (run_images overlaps two images)
+        self._banks = [None] * (len(self.engines) + 1)   # feature banks: one per fit in flight + the one being extracted
         self._stage: Optional[torch.Tensor] = None
         self._extract_stream: Optional[torch.cuda.Stream] = None
 
     # ---- HP-1 ----------------------------------------------------------------------------------------------
     def extract_bank(self, views: torch.Tensor, slot: int = 0) -> torch.Tensor:
         """views [V, 3, H, W] (cuda, or pinned host memory) -> bank [V, h, w, C] fp32 (cuda), written into bank buffer
-        `slot` (0 / 1).  Host views are copied batch by batch on a side stream into two staging buffers, so the copy of
+        `slot`.  Host views are copied batch by batch on a side stream into two staging buffers, so the copy of
         batch k+1 overlaps the forward of batch k."""
         V = views.shape[0]
         if self._banks[slot] is None or self._banks[slot].shape[0] != V:
@@ -101,30 +104,31 @@ class Stage1Pipeline:
     # ---- HP-2 ----------------------------------------------------------------------------------------------
     def denoise(self, bank: torch.Tensor, coords: torch.Tensor, idx_stream: np.ndarray,
                 init: Optional[Dict[str, torch.Tensor]] = None, seed: Optional[int] = None,
-                validate: bool = True) -> Dict[str, torch.Tensor]:
+                validate: bool = True, engine: int = 0) -> Dict[str, torch.Tensor]:
         """bank [V, h, w, C] f32 cuda, coords [V, h, w, 2] in [0,1]; the last view is the un-augmented image.
         Returns denoised_feats [1, h, w, C] (= neural_field(coords[-1]), what the reference saves) and raw [h, w, C].
         Every image starts from fresh parameters, like the reference (new SingleImageDenoiser + NeuralFeatureField per
         image, main_img_denoising.py:39-47); they are drawn on the device.  Nothing here waits for the GPU when
         validate=False (run_images), so the next image can be enqueued while this fit is running."""
         cfg = self.cfg
+        eng = self.engines[engine]
         if seed is None:
             self._image_counter += 1
             seed = (self.base_seed << 20) + self._image_counter
-        self.engine.init_params(seed)
+        eng.init_params(seed)
         if init is not None:
             for k, v in init.items():
-                self.engine.set_param(k, v)
+                eng.set_param(k, v)
         V = bank.shape[0]
-        self.engine.begin(bank.reshape(V * self.h * self.w, self.C), coords.reshape(-1, 2).to("cuda", torch.float32).contiguous(),
+        eng.begin(bank.reshape(V * self.h * self.w, self.C), coords.reshape(-1, 2).to("cuda", torch.float32).contiguous(),
                           idx_stream, lr=cfg.lr, min_lr=cfg.min_lr, warmup_iters=cfg.warmup_iters,
                           freeze_after=cfg.freeze_shared_artifacts_after, weight_decay=cfg.weight_decay,
                           loss_scale=cfg.loss_scale, validate=validate)
-        self.engine.run(graph_steps=cfg.graph_steps)
-        denoised = self.engine.query(self._full_coords, assume_valid=True).reshape(1, self.h, self.w, self.C)
+        eng.run(graph_steps=cfg.graph_steps)
+        denoised = eng.query(self._full_coords, assume_valid=True).reshape(1, self.h, self.w, self.C)
         extra = {}
         if cfg.log_losses:
-            extra["losses"] = self.engine.losses_async()      # valid once `losses_ready` has completed
+            extra["losses"] = eng.losses_async()      # valid once `losses_ready` has completed
             extra["losses_ready"] = torch.cuda.Event()
             extra["losses_ready"].record()
         # (a copy: the bank buffer is recycled for the image after next before a pipelined caller reads its result)
@@ -150,10 +154,13 @@ class Stage1Pipeline:
         stream that runs the path).  overlap=False: strictly one image after the other (for A/B measurements)."""
         if n_images <= 0:
             return []
+        ne = len(self.engines) if overlap else 1          # fits in flight
+        nslots = len(self._banks)
         if self._extract_stream is None:
             self._extract_stream = torch.cuda.Stream(priority=0)   # lowest priority: the fit's short kernels go first
-            self._ext_done = [torch.cuda.Event(), torch.cuda.Event()]
-            self._fit_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._fit_streams = [torch.cuda.Stream(priority=-1) for _ in self.engines]
+            self._ext_done = [torch.cuda.Event() for _ in range(nslots)]
+            self._fit_done = [torch.cuda.Event() for _ in range(nslots)]
         main = torch.cuda.current_stream()
         sx = self._extract_stream if overlap else main
         tev = (lambda: torch.cuda.Event(enable_timing=True)) if events is not None else None
@@ -164,8 +171,8 @@ class Stage1Pipeline:
                 return views_fn(i)
 
         def enqueue_extract(i, views):
-            slot = i % 2
-            sx.wait_event(self._fit_done[slot])    # the fit that read this bank buffer two images ago
+            slot = i % nslots
+            sx.wait_event(self._fit_done[slot])    # the fit that read this bank buffer `nslots` images ago
             with torch.cuda.stream(sx):
                 if tev:
                     a = tev()
@@ -181,35 +188,47 @@ class Stage1Pipeline:
         for e in self._fit_done:
             e.record(main)
         sx.wait_stream(main)                       # inputs produced on the caller's stream
+        for fs in self._fit_streams:
+            fs.wait_stream(main)
         results = []
         bank = enqueue_extract(0, make_views(0))
         idx = idx_fn(0)
-        pending = None                             # (i, out) of the previous image: finalised one iteration late
+        pending = []                               # (i, out) of fits in flight: finalised `ne` images late
         for i in range(n_images):
-            # The views of the NEXT image are produced now, i.e. behind the forwards of image i and in front of the fit of
-            # image i on the device time line (a low-priority kernel of 228 k tiny CTAs beside the latency-bound fit was
-            # measured to cost 250 ms).
+            # The views of the NEXT image are produced now, i.e. behind the forwards of image i on the extraction stream.
             views_next = make_views(i + 1) if i + 1 < n_images else None
-            main.wait_event(self._ext_done[i % 2])
-            if tev:
-                a = tev()
-                a.record(main)
-            out = self.denoise(bank, coords_fn(i), idx, validate=False)   # enqueue only: the host does not wait for the fit
-            if tev:
-                b = tev()
-                b.record(main)
-                events.append(("hp2", a, b))
-            self._fit_done[i % 2].record(main)
-            if i + 1 < n_images:                   # enqueued while the GPU runs the fit of image i
+            fs = self._fit_streams[i % ne] if overlap else main
+            fs.wait_event(self._ext_done[i % nslots])
+            with torch.cuda.stream(fs):
+                if tev:
+                    a = tev()
+                    a.record(fs)
+                # enqueue only: the host does not wait for the fit
+                out = self.denoise(bank, coords_fn(i), idx, validate=False, engine=i % ne)
+                if tev:
+                    b = tev()
+                    b.record(fs)
+                    events.append(("hp2", a, b))
+                self._fit_done[i % nslots].record(fs)
+                done = torch.cuda.Event()
+                done.record(fs)
+            out["_done"] = done
+            if i + 1 < n_images:                   # enqueued while the GPU runs the fits of the previous images
                 bank = enqueue_extract(i + 1, views_next)
                 idx = idx_fn(i + 1)
-            # finalize() may block (device-to-host reads): the results of image i-1 are collected only now, after image i
-            # has been enqueued completely, so the GPU always has the next fit queued behind the running one
-            if pending is not None:
-                results.append(finalize(*pending))
-            pending = (i, out)
-        if pending is not None:
-            results.append(finalize(*pending))
+            # finalize() may block (device-to-host reads): results are collected only after `ne` later fits have been
+            # enqueued completely, so the GPU always has work queued behind the running fits
+            pending.append((i, out))
+            if len(pending) > ne:
+                j, o = pending.pop(0)
+                main.wait_event(o.pop("_done"))
+                results.append(finalize(j, o))
+        for j, o in pending:
+            main.wait_event(o.pop("_done"))
+            results.append(finalize(j, o))
         main.wait_stream(sx)
-        self.engine.check()   # input validation of all fits of this call (blocks: the results are about to be read anyway)
+        for fs in self._fit_streams:
+            main.wait_stream(fs)
+        for eng in self.engines:
+            eng.check()       # input validation of all fits of this call (blocks: the results are about to be read anyway)
         return results

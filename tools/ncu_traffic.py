@@ -26,14 +26,18 @@ def main():
                          "dram_bytes": bytes_of(r, "dram__bytes_read.sum") + bytes_of(r, "dram__bytes_write.sum"),
                          "us": float(r[ix["gpu__time_duration.sum"]].replace(",", "")) *
                          {"nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(units[ix["gpu__time_duration.sum"]].lower(), 1)})
-    gem = [l for l in launches if "gemm_tn_tc_kernel" in l["kernel"]]
+    gem = [l for l in launches if "gemm_tn_cg2_kernel" in l["kernel"]]
     sweep = [l for l in launches if "fit_adam_table" in l["kernel"]]
     res = {"source": src, "launches": launches}
     if len(gem) >= 4:
-        res["gemm_tn_tc_kernel<256,3,bf16>"] = {"dram_bytes_per_launch": sum(l["dram_bytes"] for l in gem[:4]),
+        res["gemm_tn_cg2_kernel"] = {"dram_bytes_per_launch": sum(l["dram_bytes"] for l in gem[:4]),
                                                  "note": "sum over the 4-launch set (qkv, proj, fc1, fc2) at batch 16"}
     if sweep:
         res["fit_adam_table_kernel"] = {"dram_bytes_per_launch": sweep[0]["dram_bytes"]}
+    for key in ("attention_tc_kernel", "attention_bwd_tc_kernel"):
+        hit = [l for l in launches if key in l["kernel"]]
+        if hit:
+            res[key] = {"dram_bytes_per_launch": hit[0]["dram_bytes"], "us": hit[0]["us"]}
     json.dump(res, open(out, "w"), indent=1)
     print(json.dumps(res, indent=1)[:1500])
 
