@@ -46,6 +46,7 @@ struct GemmSmem {
 
 // Ragged-N tail of one 32x32 chunk (last chunk of N = 385, 129, ...): rare, so its loops stay rolled (unrolled it
 // made every kernel 130 KB; an out-of-line call was tried too and cost 30 % on the big GEMMs through ABI spills).
+template <bool FIT>
 __device__ __forceinline__ void epi_scalar_tail(const GemmEpi& e, const GemmShape& s, const float* scr, int lane, int m0,
                                              int n, bool has_k) {
 #pragma unroll 1
@@ -57,7 +58,7 @@ __device__ __forceinline__ void epi_scalar_tail(const GemmEpi& e, const GemmShap
     for (int q = 0; q < 4; ++q) {
       if (n + q >= s.N) break;
       const float x = scr[i * SCR_PITCH + (lane & 7) * 4 + q];
-      epi_post1(e, m, n + q, epi_pre(e, m, n + q, has_k ? x : 0.0f));
+      epi_post1<FIT>(e, m, n + q, epi_pre<FIT>(e, m, n + q, has_k ? x : 0.0f));
     }
   }
 }
@@ -66,6 +67,7 @@ __device__ __forceinline__ void epi_scalar_tail(const GemmEpi& e, const GemmShap
 // warp's shared-memory scratch, then the fused epilogue in the coalesced layout (each lane: 4 consecutive columns of 8
 // rows).  m0: global row of this lane's first row (tile row base + quadrant * 32 + lane / 8); n_base: global column of the
 // chunk.  Shared by the single-CTA and the CTA-pair kernels.
+template <bool FIT = false>
 __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, float* scr, int lane, const uint32_t (&r)[32],
                                           int n_base, int m0, bool has_k) {
   // ---- transpose through smem: afterwards each lane holds 4 consecutive columns of 8 rows.  No math on the
@@ -84,7 +86,7 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
     float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (e.out_mode == OUT_F32_RESID && e.gamma) g4 = __ldg(reinterpret_cast<const float4*>(e.gamma + n));
     float4 xin[8];
-    if (e.out_mode == OUT_F32_RESID) {  // issue all residual loads before any store (memory-level parallelism)
+    if (!FIT && e.out_mode == OUT_F32_RESID) {  // issue all residual loads before any store (memory-level parallelism)
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int m = m0 + 4 * jj;
@@ -92,7 +94,7 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
       }
     }
     const bool plain = e.mask == nullptr && e.mask_f32 == nullptr && e.alpha == 1.0f && has_k;
-    if (plain && e.out_mode == OUT_BF16) {
+    if (!FIT && plain && e.out_mode == OUT_BF16) {
       // ---- fast path: bias (+ GELU / ReLU) -> bf16.  The activation is chosen ONCE per chunk, the row loop is
       // branch-free (QKV and fc1+GELU, the two largest epilogues of the ViT forward).
       __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
@@ -118,7 +120,7 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
           if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
         }
       }
-    } else if (plain && e.out_mode == OUT_F32_RESID && e.act == ACT_NONE) {
+    } else if (!FIT && plain && e.out_mode == OUT_F32_RESID && e.act == ACT_NONE) {
       // ---- fast path: x += gamma * (acc + bias)  (attention out-proj, fc2) ----
       float* outp = reinterpret_cast<float*>(e.out);
 #pragma unroll
@@ -140,7 +142,7 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
       if (m >= s.M) continue;
       if (!has_k) x = make_float4(0.f, 0.f, 0.f, 0.f);
       x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-      if (e.act == ACT_GELU) {
+      if (!FIT && e.act == ACT_GELU) {
         x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
       } else if (e.act == ACT_RELU) {
         x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
@@ -148,7 +150,7 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
       if (e.mask_f32) {
         const float4 h = *reinterpret_cast<const float4*>(e.mask_f32 + (size_t)m * e.ldmask + n);
         x.x = h.x > 0.f ? x.x : 0.f; x.y = h.y > 0.f ? x.y : 0.f; x.z = h.z > 0.f ? x.z : 0.f; x.w = h.w > 0.f ? x.w : 0.f;
-      } else if (e.mask) {
+      } else if (!FIT && e.mask) {
         const uint2 hb = *reinterpret_cast<const uint2*>(e.mask + (size_t)m * e.ldmask + n);
         const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hb.x);
         const __nv_bfloat162 h23 = *reinterpret_cast<const __nv_bfloat162*>(&hb.y);
@@ -161,18 +163,18 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
         }
       }
       if (e.alpha != 1.0f) { x.x *= e.alpha; x.y *= e.alpha; x.z *= e.alpha; x.w *= e.alpha; }
-      if (e.out_mode == OUT_F32_RESID) {
+      if (!FIT && e.out_mode == OUT_F32_RESID) {
         float4 o = xin[jj];
         o.x = fmaf(g4.x, x.x, o.x); o.y = fmaf(g4.y, x.y, o.y); o.z = fmaf(g4.z, x.z, o.z); o.w = fmaf(g4.w, x.w, o.w);
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n) = o;
       } else {
-        epi_post4(e, m, n, x);
+        epi_post4<FIT>(e, m, n, x);
       }
     }
     }
   } else {
     // ---------------- ragged N tail: scalar path ----------------
-    epi_scalar_tail(e, s, scr, lane, m0, n, has_k);
+    epi_scalar_tail<FIT>(e, s, scr, lane, m0, n, has_k);
   }
   }
 
@@ -404,7 +406,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         const int n_base = tn * BN + c * 32;
         if (n_base >= s.N) continue;  // whole chunk out of range (warp-uniform)
-        epi_chunk(e, s, scr, lane, r, n_base, tm * BM + quad * 32 + (lane >> 3), has_k);
+        epi_chunk<X3>(e, s, scr, lane, r, n_base, tm * BM + quad * 32 + (lane >> 3), has_k);
         __syncwarp();
         if (ew == 0 && lane == 0) stampt(8 + (c & 7));  // chunk done (profiling aid)
       }

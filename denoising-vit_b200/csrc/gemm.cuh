@@ -57,14 +57,20 @@ struct GemmShape {
   int pdl = 0;   // launch with programmatic stream serialisation (the kernel calls pdl_wait() after its set-up)
 };
 
+// FIT = true (the 3xTF32 kernels of the stage-1 fit): epilogue features only other callers use -- GELU, the bf16 mask with
+// GELU', bf16 / residual / remapped outputs -- are compiled out.  The fit's GEMMs are small and latency bound; every
+// instruction the generic epilogue carries along was measured in their run time (profiles/r2_fit_step_ab.txt).
+template <bool FIT = false>
 __device__ __forceinline__ float epi_pre(const GemmEpi& e, int m, int n, float acc) {
   float v = acc;
   if (e.bias) v += __ldg(e.bias + n);
-  if (e.act == ACT_GELU) v = gelu_erf(v);
+  if (!FIT && e.act == ACT_GELU) v = gelu_erf(v);
   else if (e.act == ACT_RELU) v = fmaxf(v, 0.0f);
-  if (e.mask) {
-    float h = __bfloat162float(e.mask[(size_t)m * e.ldmask + n]);
-    v = e.mask_mode == 1 ? v * gelu_grad(h) : (h > 0.0f ? v : 0.0f);
+  if constexpr (!FIT) {
+    if (e.mask) {
+      float h = __bfloat162float(e.mask[(size_t)m * e.ldmask + n]);
+      v = e.mask_mode == 1 ? v * gelu_grad(h) : (h > 0.0f ? v : 0.0f);
+    }
   }
   if (e.mask_f32) v = e.mask_f32[(size_t)m * e.ldmask + n] > 0.0f ? v : 0.0f;
   return v * e.alpha;
@@ -80,8 +86,12 @@ __device__ __forceinline__ size_t epi_out_row(const GemmEpi& e, int m) {
 }
 
 // scalar post-stage (SIMT debug path and ragged tails)
+template <bool FIT = false>
 __device__ __forceinline__ void epi_post1(const GemmEpi& e, int m, int n, float v) {
-  size_t row = epi_out_row(e, m);
+  size_t row = FIT ? (size_t)m : epi_out_row(e, m);
+  if constexpr (FIT) {
+    if (e.out_mode != OUT_F32 && e.out_mode != OUT_F32_ATOMIC && e.out_mode != OUT_F32_SPLIT) return;
+  }
   switch (e.out_mode) {
     case OUT_BF16:
       reinterpret_cast<__nv_bfloat16*>(e.out)[row * e.ldo + n] = __float2bfloat16_rn(v);
@@ -113,7 +123,22 @@ __device__ __forceinline__ void epi_post1(const GemmEpi& e, int m, int n, float 
 }
 
 // vector post-stage: 4 consecutive columns, n % 4 == 0, ldo % 4 == 0, all in range
+template <bool FIT = false>
 __device__ __forceinline__ void epi_post4(const GemmEpi& e, int m, int n, float4 v) {
+  if constexpr (FIT) {   // the three output forms of the fit, nothing else
+    float* o = reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n;
+    if (e.out_mode == OUT_F32_SPLIT) {
+      const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      *reinterpret_cast<float4*>(o) = hi;
+      *reinterpret_cast<float4*>(o + e.out_plane) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    } else if (e.out_mode == OUT_F32_ATOMIC) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(o) = v;
+    }
+    return;
+  }
   size_t row = epi_out_row(e, m);
   switch (e.out_mode) {
     case OUT_BF16: {
