@@ -138,20 +138,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// prio_drop > 0: the kernel runs that many levels BELOW the highest stream priority whatever its stream's priority is
+// (kernels off the critical path that would otherwise take the SMs the next critical kernel is waiting for).
+struct LaunchOpt {
+  bool pdl = false;
+  int prio_drop = 0;
+};
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                            Args&&... args) {
+inline cudaError_t launch_kx(LaunchOpt o, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (o.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (o.prio_drop > 0) {
+    static int lo = 0, hi = 0;
+    static const cudaError_t range_rc = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (numerically lower = higher priority)
+    if (range_rc != cudaSuccess) return range_rc;
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = hi + o.prio_drop < lo ? hi + o.prio_drop : lo;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  return launch_kx(LaunchOpt{pdl, 0}, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 // ------------------------------------------------------------------------------------------------

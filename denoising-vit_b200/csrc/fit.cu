@@ -558,6 +558,7 @@ static int launch_loss(const LossArgs& la, cudaStream_t st, bool pdl) {
 // few persistent 1024-thread CTAs that fill one SM each and leave the other SMs to the GEMM chain of the next steps.
 // (Measured and rejected: one contiguous slice per CTA -- 133 us, HBM channel imbalance; maximum shared-memory
 // carve-out -- 137 us.)
+// (Measured and rejected, r2r: ld.global.cs / st.global.cs streaming hints for p, m, v -- the step got 1-4 us slower.)
 constexpr int ADAM_UNROLL = 2;
 __global__ void __launch_bounds__(1024, 1)
 fit_adam_table_kernel(TableBufs tb, size_t nvec, const AdamScalars* __restrict__ sc, const int* __restrict__ step_base,
@@ -817,6 +818,11 @@ struct Fit {
   int epoch_steps = 0;                         // pipelined steps enqueued since the sweeps were last joined
   bool enc_ready = false;                      // f->enc already holds the encoding of the next step
   int res_x3 = 1;                              // GEMM mode of the residual MLP: 1 = 3xTF32, 2 = plain TF32 (experiment)
+  int x3_wide_min_n[2] = {0, 256};             // DVT_FIT_X3_WIDE_MIN_N "p1,p2": 128 x 128 GEMM tiles when N >= this (0: never)
+  int wgrad_sms = 96;                          // DVT_FIT_WGRAD_SMS: weight-gradient GEMMs split K to fill at most this many SMs
+  bool sweep_pdl = true;                       // DVT_FIT_SWEEP_PDL=0: the persistent sweep CTAs of step t+1 are not made resident
+                                               // (waiting, one full SM each) while sweep t still runs
+  int off_path_prio_drop = 0;                  // DVT_FIT_OFFPATH_PRIO: priority levels below the chain for off-path kernels
   int wgrad_x3 = 1;                            // GEMM mode of the field MLP's weight-gradient GEMMs (DVT_FIT_WGRAD_TF32=1: 2)
   bool pdl = true;                             // programmatic dependent launch along the kernel chains of a step
   bool pipe[2] = {true, true};                 // software-pipelined table sweep in phase 1 / 2 (see fit_enqueue_step)
@@ -909,11 +915,11 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
   DVT_CUDA_OK(cudaEventCreateWithFlags(&f->ev_out, cudaEventDisableTiming));
   {
-    // Schedule knobs (defaults = the fastest measured at the headline size, profiles/r1w_fit_schedules.txt):
+    // Schedule knobs (defaults = the fastest measured at the headline size, profiles/r1w_fit_schedules.txt, r2_fit_step_ab.txt):
     //   DVT_FIT_SWEEP_CTAS="a[,b]"  per phase (1 [, 2]): n > 0 pipelined sweep on n persistent CTAs (1024 threads, one
     //                               per SM); 0 pipelined sweep on 8 x #SM CTAs of 256 threads; -1 sequential schedule
     //   DVT_FIT_PIPELINE=0          sequential schedule in both phases
-    int cfg[2] = {40, 40};
+    int cfg[2] = {48, 48};
     if (const char* se = getenv("DVT_FIT_SWEEP_CTAS")) {
       int a = 0, b = 0;
       const int got = sscanf(se, "%d,%d", &a, &b);
@@ -928,6 +934,22 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
     //   DVT_FIT_WGRAD_TF32=1        weight-gradient GEMMs of the field MLP in plain TF32 (experiment; not the default)
     const char* wt = getenv("DVT_FIT_WGRAD_TF32");
     f->wgrad_x3 = (wt && wt[0] == '1') ? 2 : 1;
+    //   DVT_FIT_SWEEP_PDL=0         sweep t+1 is launched only when sweep t has completed (no waiting resident CTAs); neutral
+    //   DVT_FIT_X3_WIDE_MIN_N="a[,b]" per phase: 3xTF32 GEMMs with N >= this use 128 x 128 tiles (0: always 128 x 64)
+    //   DVT_FIT_WGRAD_SMS=n         split-K of the weight-gradient GEMMs fills at most n SMs (they share the GPU with the
+    //                               data-gradient GEMMs of the critical path; 96: -9 us/step in phase 1, r2p)
+    //   DVT_FIT_OFFPATH_PRIO=n      launch priority of the kernels that only feed Adam(small), n levels below the chain.
+    //                               The graphs keep the attribute (checked with DVT_FIT_DEBUG_GRAPH=1) but the step time
+    //                               does not move (r2o): an SM is handed to whichever queued CTA fits first.  Default 0.
+    if (const char* sp_ = getenv("DVT_FIT_SWEEP_PDL")) f->sweep_pdl = sp_[0] != '0';
+    if (const char* wm = getenv("DVT_FIT_X3_WIDE_MIN_N")) {
+      int a = 0, b = 0;
+      const int got = sscanf(wm, "%d,%d", &a, &b);
+      if (got >= 1) f->x3_wide_min_n[0] = f->x3_wide_min_n[1] = std::max(0, a);
+      if (got == 2) f->x3_wide_min_n[1] = std::max(0, b);
+    }
+    if (const char* ws = getenv("DVT_FIT_WGRAD_SMS")) f->wgrad_sms = std::max(1, atoi(ws));
+    if (const char* op = getenv("DVT_FIT_OFFPATH_PRIO")) f->off_path_prio_drop = std::max(0, atoi(op));
     const char* rt = getenv("DVT_FIT_RES_TF32");
     f->res_x3 = (rt && rt[0] == '1') ? 2 : 1;
     const char* pd = getenv("DVT_FIT_PDL");
@@ -1352,37 +1374,41 @@ struct Op {
 
 // Y = act(X W^T + b):  X [M, K] planes, W [N, K] planes.  split_out: Y is written as hi/lo planes (feeds a GEMM).
 static int fit_linear(Op X, int M, int K, Op W, int N, const float* bias, int act, float* out, int ldo, size_t out_plane,
-                      bool split_out, cudaStream_t st, int impl, bool pdl = false, int x3 = 1) {
+                      bool split_out, cudaStream_t st, int impl, bool pdl = false, int x3 = 1, int prio_drop = 0,
+                      int wide = 0) {
   GemmEpi e;
   e.bias = bias; e.act = act; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
   e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
   GemmShape s{M, N, K, 1};
-  s.x3 = x3; s.plane_a = X.plane; s.plane_b = W.plane; s.pdl = pdl;
+  s.x3 = x3; s.plane_a = X.plane; s.plane_b = W.plane; s.pdl = pdl; s.prio_drop = prio_drop; s.x3_wide_min_n = wide;
   return launch_gemm_tn(X.p, X.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
 // dX = (dY . W) * (H > 0):  dY [M, Nout] K-major A; W stored [Nout, Kin] = MN-major B with N = Kin
 static int fit_dgrad(Op dY, int M, int Nout, Op W, int Kin, const float* Hmask, int ldmask, float* out, int ldo,
-                     size_t out_plane, bool split_out, cudaStream_t st, int impl, bool pdl = false, int x3 = 1) {
+                     size_t out_plane, bool split_out, cudaStream_t st, int impl, bool pdl = false, int x3 = 1,
+                     int prio_drop = 0, int wide = 0) {
   GemmEpi e;
   e.mask_f32 = Hmask; e.ldmask = ldmask; e.out = out; e.ldo = ldo; e.out_plane = out_plane;
   e.out_mode = split_out ? OUT_F32_SPLIT : OUT_F32;
   GemmShape s{M, Kin, Nout, 1};
-  s.b_mn = 1; s.x3 = x3; s.plane_a = dY.plane; s.plane_b = W.plane; s.pdl = pdl;
+  s.b_mn = 1; s.x3 = x3; s.plane_a = dY.plane; s.plane_b = W.plane; s.pdl = pdl; s.prio_drop = prio_drop; s.x3_wide_min_n = wide;
   return launch_gemm_tn(dY.p, dY.ld, W.p, W.ld, TMAP_F32, s, e, st, impl);
 }
 
 // dW[Nout, Kin] (+ db[Nout]) += dY^T . [X | 1]:  dY stored [n, Nout] (MN-major A), X stored [n, Kin + ones] (MN-major B)
 static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb, cudaStream_t st, int impl,
-                     bool pdl = false, int x3 = 1) {
+                     bool pdl = false, int x3 = 1, int prio_drop = 0, int wide = 0, int sm_cap = 1 << 20) {
   GemmEpi e;
   e.out = gW; e.ldo = Kin; e.out_mode = OUT_F32_ATOMIC; e.last_col_out = gb;
-  // split-K so that (output tiles x splits) fills the SMs once: tiles are 128 x 64, k-blocks 32 samples
+  // split-K so that (output tiles x splits) fills the SMs once: tiles are 128 x 64 or 128 x 128, k-blocks 32 samples
   const int kb = (n + 31) / 32;
-  const int tiles = ((Nout + 127) / 128) * ((Kin + 1 + 63) / 64);
-  int splits = std::max(1, std::min(num_sms() / std::max(tiles, 1), kb / 4));
+  const int bn = gemm_x3_tile_n(Kin + 1, wide);
+  const int tiles = ((Nout + 127) / 128) * ((Kin + bn) / bn);
+  int splits = std::max(1, std::min(std::min(num_sms(), sm_cap) / std::max(tiles, 1), kb / 4));
   GemmShape s{Nout, Kin + 1, n, splits};
-  s.a_mn = 1; s.b_mn = 1; s.x3 = x3; s.plane_a = dY.plane; s.plane_b = X.plane; s.pdl = pdl;
+  s.a_mn = 1; s.b_mn = 1; s.x3 = x3; s.plane_a = dY.plane; s.plane_b = X.plane; s.pdl = pdl; s.prio_drop = prio_drop;
+  s.x3_wide_min_n = wide;
   return launch_gemm_tn(dY.p, dY.ld, X.p, X.ld, TMAP_F32, s, e, st, impl);
 }
 
@@ -1409,10 +1435,10 @@ static int fit_launch_sweep_tma(Fit* f, int ctas, int step_off, cudaStream_t st,
 
 static int fit_launch_sweep(Fit* f, int step_off, bool phase2, cudaStream_t st) {
   if (f->sweep_tma && f->sweep_ctas[phase2 ? 1 : 0] > 0)
-    return fit_launch_sweep_tma(f, f->sweep_ctas[phase2 ? 1 : 0], step_off, st, f->pdl);
+    return fit_launch_sweep_tma(f, f->sweep_ctas[phase2 ? 1 : 0], step_off, st, f->pdl && f->sweep_pdl);
   int sg_ = 0, sb_ = 0;
   fit_sweep_geometry(f, phase2, &sg_, &sb_);
-  DVT_CUDA_OK(launch_k(f->pdl, fit_adam_table_kernel, dim3(sg_), dim3(sb_), 0, st, f->tb, f->n_table / 4, f->sc_main,
+  DVT_CUDA_OK(launch_k(f->pdl && f->sweep_pdl, fit_adam_table_kernel, dim3(sg_), dim3(sb_), 0, st, f->tb, f->n_table / 4, f->sc_main,
                        f->step_base, step_off, f->wd));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -1459,6 +1485,13 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   const Op dR{f->dR, C, p_nc}, dr2{f->dr2, Hr, p_nr}, dr1{f->dr1, Hr, p_nr};
   cudaStream_t sB = f->sB, sC = f->sC, sD = f->sD, sE = f->sE;
   const bool pdl = f->pdl;
+  // Kernels that only feed Adam(small) -- weight gradients, the residual MLP's backward, the dG scatter -- can be launched
+  // below the chain's priority (DVT_FIT_OFFPATH_PRIO; measured neutral, see fit_create).  What does help is keeping the
+  // weight-gradient GEMMs small (wcap): the CUPTI timeline (tools/fit_timeline.py) shows the next kernel of the critical
+  // path waiting one CTA lifetime (~12 us, twice per step) whenever a finishing data-gradient GEMM hands its SMs to the
+  // queued CTAs of a weight-gradient GEMM -- every 3xTF32 CTA fills the shared memory of its SM.
+  const int off = f->off_path_prio_drop;
+  const int wide = f->x3_wide_min_n[phase2 ? 1 : 0], wcap = f->wgrad_sms;
   auto fork = [&](cudaStream_t to, cudaEvent_t e) -> int {
     DVT_CUDA_OK(cudaEventRecord(e, st));
     DVT_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
@@ -1477,12 +1510,12 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   const bool pipe = f->pipe[phase2 ? 1 : 0];
   if (!pipe) FIT_RC(fit_enqueue_encode(f, step_off, 0, st));  // else f->enc is already this step's (fit_run)
   if (phase2) {
-    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl, pdl, f->res_x3));
-    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl, pdl, f->res_x3));
-    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl, pdl, f->res_x3));
+    FIT_RC(fit_linear(rawb, n, C, W(f->R1), Hr, sp + f->rb1.off, ACT_RELU, f->r1, f->ld_r, p_r, true, sB, impl, pdl, f->res_x3, 0, wide));
+    FIT_RC(fit_linear(r1, n, Hr, W(f->R2), Hr, sp + f->rb2.off, ACT_RELU, f->r2, f->ld_r, p_r, true, sB, impl, pdl, f->res_x3, 0, wide));
+    FIT_RC(fit_linear(r2, n, Hr, W(f->R3), C, sp + f->rb3.off, ACT_NONE, f->Rout, C, 0, false, sB, impl, pdl, f->res_x3, 0, wide));
   }
-  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl, pdl));
-  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl, pdl));
+  FIT_RC(fit_linear(enc, n, Lf, W(f->W1), H1, sp + f->b1.off, ACT_RELU, f->h1, f->ld_h1, p_h1, true, st, impl, pdl, 1, 0, wide));
+  FIT_RC(fit_linear(h1, n, H1, W(f->W2), C, sp + f->b2.off, ACT_NONE, f->Fout, C, 0, false, st, impl, pdl, 1, 0, wide));
   FIT_RC(join(sB, f->ev[1]));
   // ---- loss + d pred ----
   LossArgs la;
@@ -1498,11 +1531,11 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
     FIT_RC(fork(sC, f->ev[3]));
     FIT_RC(fork(sE, f->ev[11]));
   }
-  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl, pdl, f->wgrad_x3));          // side B
-  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl, pdl));  // main
+  FIT_RC(fit_wgrad(dpred, n, C, h1, H1, sg + f->W2.off, sg + f->b2.off, sB, impl, pdl, f->wgrad_x3, off, wide, wcap));   // side B
+  FIT_RC(fit_dgrad(dpred, n, C, W(f->W2), H1, f->h1, f->ld_h1, f->dh1, H1, p_nh, true, st, impl, pdl, 1, 0, wide));  // main
   FIT_RC(fork(sB, f->ev[4]));  // dh1 ready
-  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl, pdl, f->wgrad_x3));           // side B (reads enc)
-  FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl, pdl));
+  FIT_RC(fit_wgrad(dh1, n, H1, enc, Lf, sg + f->W1.off, sg + f->b1.off, sB, impl, pdl, f->wgrad_x3, off, wide, wcap));  // side B (reads enc)
+  FIT_RC(fit_dgrad(dh1, n, H1, W(f->W1), Lf, nullptr, 0, f->denc, Lf, 0, false, st, impl, pdl, 1, 0, wide));
   if (!phase2) {
     // dG (+ grid_sample's neighbour shares) on side C, enqueued BEHIND the two data-gradient GEMMs: launched beside them, its
     // 256 small CTAs take the registers the GEMM CTAs need and delay the critical path by ~10 us (measured, r2i)
@@ -1510,7 +1543,7 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
     ScatterArgs sa;
     sa.dpred = f->dpred; sa.plane = p_nc; sa.sr = sr; sa.gG = sg + f->G.off; sa.n = n; sa.C = C; sa.hw = f->hw;
     sa.gw = f->gw; sa.gh = f->gh; sa.ax_i0 = f->ax_i0; sa.ax_w0 = f->ax_w0; sa.ax_w1 = f->ax_w1;
-    DVT_CUDA_OK(launch_k(pdl, fit_g_scatter_kernel, dim3((n * 32 + tb - 1) / tb), dim3(tb), 0, sC, sa));
+    DVT_CUDA_OK(launch_kx(LaunchOpt{pdl, off}, fit_g_scatter_kernel, dim3((n * 32 + tb - 1) / tb), dim3(tb), 0, sC, sa));
     DVT_CUDA_OK(cudaGetLastError());
     count_launch();
   }
@@ -1525,13 +1558,13 @@ static int fit_enqueue_step(Fit* f, int step_off, bool phase2, cudaStream_t st, 
   if (phase2) {
     // residual MLP backward: the data-gradient chain on side C, the weight-gradient GEMMs that do not feed it on side E
     //   side C: dr2 = dR.R3 -> dr1 = dr2.R2 -> dR1      side E: dR3 (needs dR, r2 only) -> [dr2 ready] dR2
-    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, sC, impl, pdl, f->res_x3));
+    FIT_RC(fit_dgrad(dR, n, C, W(f->R3), Hr, f->r2, f->ld_r, f->dr2, Hr, p_nr, true, sC, impl, pdl, f->res_x3, off, wide));
     DVT_CUDA_OK(cudaEventRecord(f->ev[12], sC));                                              // dr2 ready
-    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, sC, impl, pdl, f->res_x3));
-    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl, pdl, f->res_x3));
-    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sE, impl, pdl, f->res_x3));
+    FIT_RC(fit_dgrad(dr2, n, Hr, W(f->R2), Hr, f->r1, f->ld_r, f->dr1, Hr, p_nr, true, sC, impl, pdl, f->res_x3, off, wide));
+    FIT_RC(fit_wgrad(dr1, n, Hr, rawb, C, sg + f->R1.off, sg + f->rb1.off, sC, impl, pdl, f->res_x3, off, wide, wcap));
+    FIT_RC(fit_wgrad(dR, n, C, r2, Hr, sg + f->R3.off, sg + f->rb3.off, sE, impl, pdl, f->res_x3, off, wide, wcap));
     DVT_CUDA_OK(cudaStreamWaitEvent(sE, f->ev[12], 0));
-    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sE, impl, pdl, f->res_x3));
+    FIT_RC(fit_wgrad(dr2, n, Hr, r1, Hr, sg + f->R2.off, sg + f->rb2.off, sE, impl, pdl, f->res_x3, off, wide, wcap));
     FIT_RC(join(sE, f->ev[13]));
   }
   FIT_RC(join(sC, f->ev[5]));
@@ -1592,6 +1625,30 @@ static int fit_capture(Fit* f, bool phase2, int steps, cudaStream_t st, int impl
     return rc;
   }
   DVT_CUDA_OK(e);
+  if (getenv("DVT_FIT_DEBUG_GRAPH")) {  // what the capture recorded: kernel nodes per priority, programmatic edges
+    size_t nn = 0, ne = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    std::vector<cudaGraphNode_t> nodes_v(nn);
+    cudaGraphGetNodes(graph, nodes_v.data(), &nn);
+    int hist[16] = {}, kernels = 0;
+    for (auto nd : nodes_v) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+      cudaLaunchAttributeValue v = {};
+      if (cudaGraphKernelNodeGetAttribute(nd, cudaLaunchAttributePriority, &v) == cudaSuccess) hist[std::min(15, std::abs(v.priority))] += 1;
+      ++kernels;
+    }
+    cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &ne);
+    std::vector<cudaGraphNode_t> from(ne), to(ne);
+    std::vector<cudaGraphEdgeData> ed(ne);
+    int prog = 0;
+    if (cudaGraphGetEdges_v2(graph, from.data(), to.data(), ed.data(), &ne) == cudaSuccess)
+      for (auto& d : ed) prog += d.type == cudaGraphDependencyTypeProgrammatic;
+    fprintf(stderr, "[dvt fit graph] phase %d: %zu nodes, %d kernels, |priority| histogram:", phase2 ? 2 : 1, nn, kernels);
+    for (int i = 0; i < 16; ++i) if (hist[i]) fprintf(stderr, " %d:%d", i, hist[i]);
+    fprintf(stderr, "; %zu edges, %d programmatic\n", ne, prog);
+    cudaGetLastError();
+  }
   e = cudaGraphInstantiate(out, graph, 0);
   cudaGraphDestroy(graph);
   DVT_CUDA_OK(e);

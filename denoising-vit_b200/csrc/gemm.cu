@@ -25,7 +25,8 @@ constexpr int KB_BYTES = 128;  // bytes of K per pipeline stage row (= one 128B 
 // memory-level parallelism of one warp per scheduler).  The x3 (fit) kernels use 128x64 tiles: their problems are small
 // (M = 2048), so narrower tiles mean more CTAs, half the MMA time per k-block and a one-chunk-per-warp epilogue.
 // The 128x256 bf16 tiles (HP-1) get 12 epilogue warps: their GELU / residual epilogues are ALU- and latency-bound.
-constexpr int epi_warps(int bn, bool x3) { return (bn == 256 && !x3) ? 12 : 8; }
+// The 128x128 x3 tiles keep three 64 KB stages: only four epilogue warps' transpose scratch fits beside them.
+constexpr int epi_warps(int bn, bool x3) { return (bn == 256 && !x3) ? 12 : (x3 && bn == 128) ? 4 : 8; }
 constexpr int SCR_PITCH = 36;  // floats; 16B-aligned rows, conflict-free for the access pattern below
 
 template <int BN, int STAGES, bool X3 = false>
@@ -486,7 +487,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s
     tiles_per_cta = v ? atoi(v) : 0;
   }
   if (!X3 && tiles_per_cta > 0) grid = std::max(grid, (tiles + tiles_per_cta - 1) / tiles_per_cta);
-  DVT_CUDA_OK(launch_k(s.pdl != 0, kern, dim3(grid), dim3(L::THREADS), (size_t)L::TOTAL, stream, tmA, tmB, s, e));
+  DVT_CUDA_OK(launch_kx(LaunchOpt{s.pdl != 0, s.prio_drop}, kern, dim3(grid), dim3(L::THREADS), (size_t)L::TOTAL, stream, tmA, tmB, s, e));
   count_launch();
   DVT_CUDA_OK(cudaGetLastError());
   return DVT_OK;
@@ -517,9 +518,18 @@ int gemm_prepare() {
   if ((rc = prep_one<64, 3, true, false, false, true>())) return rc;
   if ((rc = prep_one<64, 3, true, false, true, true>())) return rc;
   if ((rc = prep_one<64, 3, true, true, true, true>())) return rc;
+  if ((rc = prep_one<128, 3, true, false, false, true>())) return rc;
+  if ((rc = prep_one<128, 3, true, false, true, true>())) return rc;
+  if ((rc = prep_one<128, 3, true, true, true, true>())) return rc;
   done = true;
   return DVT_OK;
 }
+
+// Tile width of the 3xTF32 kernels.  Measured on the fit's shapes (tools/gemm_timeline.py): a k-block costs ~0.66 us with
+// 12 MMAs whether the tile is 128 x 64 or 128 x 128 (each 128 x N x 8 TF32 instruction takes ~78 clk for N <= 128), so the
+// wide tile halves the tensor time and moves a third less operand data through L2 per flop; the narrow tile gives twice
+// the CTAs and the shorter epilogue.  The caller chooses per call (GemmShape::x3_wide_min_n; 0 = always 128 x 64).
+int gemm_x3_tile_n(int N, int wide_min_n) { return (wide_min_n > 0 && N >= wide_min_n) ? 128 : 64; }
 
 int default_gemm_impl() {
   static int impl = -1;
@@ -570,12 +580,18 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
                 "gemm: x3 pitches must be multiples of 16 bytes");
     CUtensorMap tA, tB;
     int rc3;
+    const int bn3 = gemm_x3_tile_n(s.N, s.x3_wide_min_n);
     if (s.a_mn) rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.M, (uint64_t)s.K, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, 32, 2, true);
     else rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.K, (uint64_t)s.M, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, BM, 2);
     if (rc3) return rc3;
     if (s.b_mn) rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.N, (uint64_t)s.K, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 32, 2, true);
-    else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 64, 2);
+    else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, bn3, 2);
     if (rc3) return rc3;
+    if (bn3 == 128) {
+      if (s.a_mn) return launch_tc<128, 3, true, true, true, true>(tA, tB, s, epi, stream);
+      if (s.b_mn) return launch_tc<128, 3, true, false, true, true>(tA, tB, s, epi, stream);
+      return launch_tc<128, 3, true, false, false, true>(tA, tB, s, epi, stream);
+    }
     if (s.a_mn) return launch_tc<64, 3, true, true, true, true>(tA, tB, s, epi, stream);
     if (s.b_mn) return launch_tc<64, 3, true, false, true, true>(tA, tB, s, epi, stream);
     return launch_tc<64, 3, true, false, false, true>(tA, tB, s, epi, stream);

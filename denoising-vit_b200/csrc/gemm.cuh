@@ -55,6 +55,8 @@ struct GemmShape {
   int x3 = 0;    // 1: 3xTF32 as described; 2: same operand layout, but only A_hi.B_hi (plain TF32 accuracy)
   size_t plane_a = 0, plane_b = 0;
   int pdl = 0;   // launch with programmatic stream serialisation (the kernel calls pdl_wait() after its set-up)
+  int x3_wide_min_n = 0;  // x3: 128 x 128 tiles when N >= this (0: always 128 x 64)
+  int prio_drop = 0;  // > 0: launch that many priority levels below the highest (common.cuh LaunchOpt)
 };
 
 // FIT = true (the 3xTF32 kernels of the stage-1 fit): epilogue features only other callers use -- GELU, the bf16 mask with
@@ -198,5 +200,6 @@ bool gemm_cg2_enabled();
 
 int default_gemm_impl();
 int gemm_prepare();
+int gemm_x3_tile_n(int N, int wide_min_n);  // 64 or 128: tile width launch_gemm_tn picks for a 3xTF32 product
 
 }  // namespace dvt
