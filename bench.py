@@ -115,7 +115,7 @@ def kernel_rooflines(pipe, extract_bsz, dev):
 
     gemm_ms = [time_alone(fn) for fn in gemms]
     gemm_flops = Bv * (4.85e9 + 1.62e9 + 12.93e9)
-    sweep_ctas = int(os.environ.get("DVT_FIT_SWEEP_CTAS", "40").split(",")[0])  # geometry of the timed region (fit.cu default)
+    sweep_ctas = int(os.environ.get("DVT_FIT_SWEEP_CTAS", "48").split(",")[0])  # geometry of the timed region (fit.cu default)
     del flush
 
     def time_stream(fn, reps=20, warm=3):

@@ -3,7 +3,7 @@
   ncu --set full --clock-control none --import-source on --profile-from-start off -o <rep> python tools/ncu_targets.py
 Order of the captured launches: GEMM qkv, out-proj(+residual), fc1(+GELU), fc2(+residual) of one ViT-B block at
 batch 16 (gemm_tn_cg2_kernel: bf16, CTA pairs), then the dense Adam sweep of the full-size hash table on the full grid and
-on 40 persistent CTAs (fit_adam_table_kernel, the geometry of the timed region), the fit's largest 3xTF32 GEMM
+on 48 persistent CTAs (fit_adam_table_kernel, the geometry of the timed region), the fit's largest 3xTF32 GEMM
 (F = h1 W2^T: M 2048, N 768, K 384), flash attention forward (+lse) and backward at batch 16 x 12 heads x 1370 tokens.
 tools/ncu_traffic.py turns the report into profiles/traffic.json."""
 import os
@@ -51,7 +51,7 @@ def main():
     qkv = rn(B, N, 3 * C).bfloat16()
     att, lse = train_ops.attention_fwd_lse(qkv, 12)
     datt = rn(B, N, C).bfloat16()
-    targets = gemms + [lambda: eng.sweep_once(0), lambda: eng.sweep_once(-40), lambda: ops.gemm_f32x3(a2, b2, 2048, 768, 384),
+    targets = gemms + [lambda: eng.sweep_once(0), lambda: eng.sweep_once(-48), lambda: ops.gemm_f32x3(a2, b2, 2048, 768, 384),
                        lambda: train_ops.attention_fwd_lse(qkv, 12), lambda: train_ops.attention_bwd(qkv, att, datt, lse, 12)]
     for fn in targets:          # warm-up (module load, attribute opt-in)
         fn()
