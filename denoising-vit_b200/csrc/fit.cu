@@ -818,6 +818,8 @@ struct Fit {
   int epoch_steps = 0;                         // pipelined steps enqueued since the sweeps were last joined
   bool enc_ready = false;                      // f->enc already holds the encoding of the next step
   int res_x3 = 1;                              // GEMM mode of the residual MLP: 1 = 3xTF32, 2 = plain TF32 (experiment)
+  int sweep_threads = 1024;                    // DVT_FIT_SWEEP_THREADS: threads of a persistent sweep CTA (1024 fills the register file of
+                                               // its SM; 512 leaves half of it to co-resident CTAs of the chain)
   int x3_wide_min_n[2] = {0, 256};             // DVT_FIT_X3_WIDE_MIN_N "p1,p2": 128 x 128 GEMM tiles when N >= this (0: never)
   int wgrad_sms = 96;                          // DVT_FIT_WGRAD_SMS: weight-gradient GEMMs split K to fill at most this many SMs
   bool sweep_pdl = true;                       // DVT_FIT_SWEEP_PDL=0: the persistent sweep CTAs of step t+1 are not made resident
@@ -880,6 +882,38 @@ struct Fit {
   std::vector<void*> owned;
 };
 
+// EXPERIMENT (DVT_FIT_CARVEOUT=1; off by default).  Every 3xTF32 GEMM CTA of the chain needs 181-212 KB of shared memory, and
+// an SM changes its L1 / shared-memory split only when it is idle: a GEMM CTA cannot join an SM on which one of the fit's
+// small kernels (no shared memory, so by default the largest L1) got first -- it waits until those CTAs have drained.  Seen
+// in the CUPTI timeline (r2u): with one 512-thread sweep CTA on EVERY SM (DVT_FIT_SWEEP_THREADS=512, DVT_FIT_SWEEP_CTAS=148)
+// no GEMM CTA started before the sweep had finished.  Asking for the maximum shared-memory carve-out on the fit's own
+// kernels does make the GEMM CTAs resident beside them, but the loads in flight of the sweep / encode / loss kernels live
+// in L1: with 28 KB of it the 48-CTA sweep takes 286 us instead of 145 and the step 218 us instead of 156; the co-resident
+// geometry reaches 185 us (r2v).  Rejected: the sweep keeps its own SMs and the driver's default split.
+static int fit_prepare_kernels() {
+  static bool done = false;
+  if (done) return DVT_OK;
+  done = true;
+  const char* e = getenv("DVT_FIT_CARVEOUT");
+  if (!(e && e[0] == '1')) return DVT_OK;
+#define DVT_MAX_SHARED(k) DVT_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+  DVT_MAX_SHARED(fit_encode_kernel);
+  DVT_MAX_SHARED(fit_grid_bwd_kernel);
+  DVT_MAX_SHARED(fit_gather_rows_kernel);
+  DVT_MAX_SHARED(fit_g_scatter_kernel);
+  DVT_MAX_SHARED(fit_adam_table_kernel);
+  DVT_MAX_SHARED(fit_adam_small_kernel);
+  DVT_MAX_SHARED(fit_advance_kernel);
+  DVT_MAX_SHARED((fit_loss_kernel<1, false>)); DVT_MAX_SHARED((fit_loss_kernel<1, true>));
+  DVT_MAX_SHARED((fit_loss_kernel<2, false>)); DVT_MAX_SHARED((fit_loss_kernel<2, true>));
+  DVT_MAX_SHARED((fit_loss_kernel<3, false>)); DVT_MAX_SHARED((fit_loss_kernel<3, true>));
+  DVT_MAX_SHARED((fit_loss_kernel<6, false>)); DVT_MAX_SHARED((fit_loss_kernel<6, true>));
+  DVT_MAX_SHARED((fit_loss_kernel<8, false>)); DVT_MAX_SHARED((fit_loss_kernel<8, true>));
+  DVT_MAX_SHARED((fit_loss_kernel<12, false>)); DVT_MAX_SHARED((fit_loss_kernel<12, true>));
+#undef DVT_MAX_SHARED
+  return DVT_OK;
+}
+
 static int fit_alloc(Fit* f, void** p, size_t bytes, bool zero = true) {
   DVT_CUDA_OK(cudaMalloc(p, bytes));
   f->owned.push_back(*p);
@@ -897,6 +931,8 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
   DVT_REQUIRE(gh > 0 && gw > 0, "fit: bad noise-map size");
   {
     int prc = gemm_prepare();
+    if (prc) return prc;
+    prc = fit_prepare_kernels();
     if (prc) return prc;
   }
   Fit* f = new Fit();
@@ -948,6 +984,7 @@ int fit_create(Fit** out, int C, int gh, int gw, int bsz, int n_levels, const fl
       if (got >= 1) f->x3_wide_min_n[0] = f->x3_wide_min_n[1] = std::max(0, a);
       if (got == 2) f->x3_wide_min_n[1] = std::max(0, b);
     }
+    if (const char* st_ = getenv("DVT_FIT_SWEEP_THREADS")) f->sweep_threads = std::min(1024, std::max(128, atoi(st_) / 32 * 32));
     if (const char* ws = getenv("DVT_FIT_WGRAD_SMS")) f->wgrad_sms = std::max(1, atoi(ws));
     if (const char* op = getenv("DVT_FIT_OFFPATH_PRIO")) f->off_path_prio_drop = std::max(0, atoi(op));
     const char* rt = getenv("DVT_FIT_RES_TF32");
@@ -1416,7 +1453,7 @@ static int fit_wgrad(Op dY, int n, int Nout, Op X, int Kin, float* gW, float* gb
 // chain of the next steps keeps the other SMs), else 8 x #SM CTAs of 256 threads (fastest when running alone).
 static void fit_sweep_geometry(const Fit* f, bool phase2, int* grid, int* block) {
   const int ctas = f->sweep_ctas[phase2 ? 1 : 0];
-  if (ctas > 0) { *grid = ctas; *block = 1024; }
+  if (ctas > 0) { *grid = ctas; *block = f->sweep_threads; }
   else { *grid = num_sms() * 8; *block = 256; }
 }
 
