@@ -882,7 +882,7 @@ struct Fit {
   std::vector<void*> owned;
 };
 
-// EXPERIMENT (DVT_FIT_CARVEOUT=1; off by default).  Every 3xTF32 GEMM CTA of the chain needs 181-212 KB of shared memory, and
+// EXPERIMENT (DVT_FIT_CARVEOUT=<percent> for the small kernels, DVT_FIT_CARVEOUT_SWEEP=<percent> for the sweep; off by default).  Every 3xTF32 GEMM CTA of the chain needs 181-212 KB of shared memory, and
 // an SM changes its L1 / shared-memory split only when it is idle: a GEMM CTA cannot join an SM on which one of the fit's
 // small kernels (no shared memory, so by default the largest L1) got first -- it waits until those CTAs have drained.  Seen
 // in the CUPTI timeline (r2u): with one 512-thread sweep CTA on EVERY SM (DVT_FIT_SWEEP_THREADS=512, DVT_FIT_SWEEP_CTAS=148)
@@ -894,14 +894,17 @@ static int fit_prepare_kernels() {
   static bool done = false;
   if (done) return DVT_OK;
   done = true;
-  const char* e = getenv("DVT_FIT_CARVEOUT");
-  if (!(e && e[0] == '1')) return DVT_OK;
-#define DVT_MAX_SHARED(k) DVT_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+  const char* e = getenv("DVT_FIT_CARVEOUT");            // percent of the unified L1 / shared array, small kernels
+  const char* es = getenv("DVT_FIT_CARVEOUT_SWEEP");     // ... the sweep
+  const int pct = e ? atoi(e) : 0, pct_sweep = es ? atoi(es) : 0;
+#define DVT_MAX_SHARED(k) DVT_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct))
+  if (pct_sweep > 0)
+    DVT_CUDA_OK(cudaFuncSetAttribute(fit_adam_table_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct_sweep));
+  if (pct <= 0) return DVT_OK;
   DVT_MAX_SHARED(fit_encode_kernel);
   DVT_MAX_SHARED(fit_grid_bwd_kernel);
   DVT_MAX_SHARED(fit_gather_rows_kernel);
   DVT_MAX_SHARED(fit_g_scatter_kernel);
-  DVT_MAX_SHARED(fit_adam_table_kernel);
   DVT_MAX_SHARED(fit_adam_small_kernel);
   DVT_MAX_SHARED(fit_advance_kernel);
   DVT_MAX_SHARED((fit_loss_kernel<1, false>)); DVT_MAX_SHARED((fit_loss_kernel<1, true>));
