@@ -365,7 +365,22 @@ __device__ __forceinline__ float fast_erf(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
   return copysignf(1.0f - e, x);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+// GELU(x) = x Phi(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2): with erfc = 2^q as in fast_erf (same polynomial, written in
+// a = |x| with the -1 of the factor 0.5 folded into the exponent) this is 11 instructions per element instead of 18 -- the
+// fc1 epilogue is issue bound (ncu: issue 50 %, tensor 51 %).  Max abs error vs the exact erf GELU 5.2e-7.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float a = fminf(fabsf(x), 8.485281374f);
+  float q = 1.9755745359180961e-05f;
+  q = fmaf(q, a, -6.6162906245512902e-04f);
+  q = fmaf(q, a, 7.7581320540732555e-03f);
+  q = fmaf(q, a, -5.2962877549126521e-02f);
+  q = fmaf(q, a, -4.5906686494096666e-01f);
+  q = fmaf(q, a, -1.1511190142292334f);
+  q = fmaf(q, a, -1.0f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return fmaf(-a, e, fmaxf(x, 0.0f));
+}
 
 // d/dx gelu_erf(x) = Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_grad(float x) {
