@@ -190,9 +190,16 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int BK = KB_BYTES / ELEM;         // elements of K per stage
   constexpr int UMMA_K_BYTES = 32;            // K=16 bf16 or K=8 tf32 per instruction
   constexpr int MMAS_PER_STAGE = KB_BYTES / UMMA_K_BYTES;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                 : (2 * BN <= 256) ? 256 : 512;
-  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+  // x3 with a K-major B: the hi and lo planes of a B tile are adjacent [BN x 128 B] blocks, i.e. ONE K-major tile of 2 BN
+  // rows.  A_hi . [B_hi | B_lo] is therefore a single MMA of width 2 BN whose accumulator holds hi.hi in columns [0, BN) and
+  // hi.lo in [BN, 2 BN); A_lo . B_hi accumulates into the first half and the epilogue adds the halves.  Two instructions
+  // per k-step instead of three: a 128 x N x 8 TF32 MMA costs ~78 clk for any N <= 128 (tools/gemm_timeline.py), so the
+  // k-block gets a quarter cheaper.  (MN-major B tiles interleave the planes per 32-column atom: three MMAs as before.)
+  constexpr bool CAT = X3 && !B_MN && 4 * BN <= 512;
+  constexpr int ACC_W = CAT ? 2 * BN : BN;  // TMEM columns of one accumulator stage
+  constexpr uint32_t TMEM_COLS = (2 * ACC_W <= 32) ? 32 : (2 * ACC_W <= 64) ? 64 : (2 * ACC_W <= 128) ? 128
+                                 : (2 * ACC_W <= 256) ? 256 : 512;
+  static_assert(2 * ACC_W <= 512, "two accumulator stages must fit TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -319,7 +326,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         mbar_wait(&tempty[as], aphase ^ 1, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * ACC_W;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
@@ -343,7 +350,11 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint64_t dah = make_smem_desc(a_base + ka, lbo_a, sbo_a, lt_a), dal = make_smem_desc(a_lo + ka, lbo_a, sbo_a, lt_a);
               const uint64_t dbh = make_smem_desc(b_base + kbb, lbo_b, sbo_b, lt_b), dbl = make_smem_desc(b_lo + kbb, lbo_b, sbo_b, lt_b);
               const uint32_t acc0 = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (s.x3 == 1) {
+              if (CAT && s.x3 == 1) {
+                constexpr uint32_t idesc_cat = make_idesc(2u, BM, 2 * BN, 0u, 0u);
+                umma_tf32(d_tmem, dah, dbh, idesc_cat, acc0);  // [hi.hi | hi.lo]: the descriptor at B_hi spans both planes
+                umma_tf32(d_tmem, dal, dbh, idesc, 1u);        // + lo.hi
+              } else if (s.x3 == 1) {
                 umma_tf32(d_tmem, dal, dbh, idesc, acc0);  // small terms first
                 umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                 umma_tf32(d_tmem, dah, dbh, idesc, 1u);
@@ -395,12 +406,20 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
       if (ew == 0 && lane == 0) stampt(4);  // accumulator ready, epilogue starts
-      const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quad * 32) << 16) + as * ACC_W;
 #pragma unroll 1
       for (int c = c_first; c < BN / 32; c += CSTEP) {
         uint32_t r[32];
         tmem_ld_32x32(taddr_row + c * 32, r);
-        tmem_ld_wait();
+        if (CAT && s.x3 == 1) {
+          uint32_t r2[32];
+          tmem_ld_32x32(taddr_row + BN + c * 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        } else {
+          tmem_ld_wait();
+        }
         if (c + CSTEP >= BN / 32) {  // this warp's last read of the accumulator stage
           tc_fence_before();
           mbar_arrive(&tempty[as]);
