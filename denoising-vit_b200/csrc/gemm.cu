@@ -194,8 +194,10 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // rows.  A_hi . [B_hi | B_lo] is therefore a single MMA of width 2 BN whose accumulator holds hi.hi in columns [0, BN) and
   // hi.lo in [BN, 2 BN); A_lo . B_hi accumulates into the first half and the epilogue adds the halves.  Two instructions
   // per k-step instead of three: a 128 x N x 8 TF32 MMA costs ~78 clk for any N <= 128 (tools/gemm_timeline.py), so the
-  // k-block gets a quarter cheaper.  (MN-major B tiles interleave the planes per 32-column atom: three MMAs as before.)
-  constexpr bool CAT = X3 && !B_MN && 4 * BN <= 512;
+  // k-block gets a quarter cheaper.  An MN-major B tile is made of 32-column atoms ([32 k-rows][32 mn] = 4 KB each); for the
+  // same trick its atoms are loaded plane by plane -- [plane][atom] instead of [atom][plane] -- so that the lo atoms
+  // continue the hi atoms at the same 4 KB stride (one more TMA instruction per atom, same bytes).
+  constexpr bool CAT = X3 && 4 * BN <= 512;
   constexpr int ACC_W = CAT ? 2 * BN : BN;  // TMEM columns of one accumulator stage
   constexpr uint32_t TMEM_COLS = (2 * ACC_W <= 32) ? 32 : (2 * ACC_W <= 64) ? 64 : (2 * ACC_W <= 128) ? 128
                                  : (2 * ACC_W <= 256) ? 256 : 512;
@@ -282,9 +284,12 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_3d(sA + stage * L::A_BYTES, &tmA, &full[stage], kb * BK, tm * BM, 0);
             }
             if (B_MN) {
+              // (tensor map box = ONE plane of an atom: launch_gemm_tn)
 #pragma unroll
-              for (int a = 0; a < BN / 32; ++a)
-                tma_load_3d(sB + stage * L::B_BYTES + a * 8192, &tmB, &full[stage], tn * BN + a * 32, kb * BK, 0);
+              for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                for (int a = 0; a < BN / 32; ++a)
+                  tma_load_3d(sB + stage * L::B_BYTES + (pl * (BN / 32) + a) * 4096, &tmB, &full[stage], tn * BN + a * 32, kb * BK, pl);
             } else {
               tma_load_3d(sB + stage * L::B_BYTES, &tmB, &full[stage], kb * BK, tn * BN, 0);
             }
@@ -334,14 +339,15 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // K-major: rows of 128 B (one swizzle atom of K), 8-row groups 1024 B apart; K advances 32 B per MMA.
           // MN-major (bf16): tile = [MN/64 atoms][BK k-rows][64 mn]; atoms BK*128 B apart (LBO), 8-k groups 1024 B
           // apart (SBO); K advances 16 rows = 2048 B per MMA.
-          // x3 (fp32 hi/lo planes): K-major tile = [plane][rows][128 B]; MN-major tile = [MN/32 atoms][plane][32 k-rows]
-          // [32 mn] (atoms 8192 B apart, lo plane +4096 B, K advances 8 rows = 1024 B per MMA).  MN-major TF32 operands
+          // x3 (fp32 hi/lo planes): K-major tile = [plane][rows][128 B]; MN-major A tile = [MN/32 atoms][plane][32 k-rows]
+          // [32 mn] (atoms 8192 B apart, lo plane +4096 B), MN-major B tile = [plane][MN/32 atoms][32 k-rows][32 mn] (atoms
+          // 4096 B apart, lo plane after the hi atoms); K advances 8 rows = 1024 B per MMA.  MN-major TF32 operands
           // must use the "128B swizzle with 32B atoms" layout (descriptor layout type 1, TMA SWIZZLE_128B_ATOM_32B):
           // the swizzle pattern repeats every 4 K-rows, so the stride between K groups (SBO) is 512 B.
           const uint32_t a_base = smem_u32(sA + stage * L::A_BYTES), b_base = smem_u32(sB + stage * L::B_BYTES);
           if (X3) {
-            const uint32_t a_lo = a_base + (A_MN ? 4096 : BM * KB_BYTES), b_lo = b_base + (B_MN ? 4096 : BN * KB_BYTES);
-            const uint32_t lbo_a = A_MN ? 8192 : 0, lbo_b = B_MN ? 8192 : 0;
+            const uint32_t a_lo = a_base + (A_MN ? 4096 : BM * KB_BYTES), b_lo = b_base + (B_MN ? (BN / 32) * 4096 : BN * KB_BYTES);
+            const uint32_t lbo_a = A_MN ? 8192 : 0, lbo_b = B_MN ? 4096 : 0;
 #pragma unroll
             for (int k = 0; k < MMAS_PER_STAGE; ++k) {
               const uint32_t ka = A_MN ? k * 1024 : k * UMMA_K_BYTES, kbb = B_MN ? k * 1024 : k * UMMA_K_BYTES;
@@ -351,7 +357,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint64_t dbh = make_smem_desc(b_base + kbb, lbo_b, sbo_b, lt_b), dbl = make_smem_desc(b_lo + kbb, lbo_b, sbo_b, lt_b);
               const uint32_t acc0 = (kb > kb0 || k > 0) ? 1u : 0u;
               if (CAT && s.x3 == 1) {
-                constexpr uint32_t idesc_cat = make_idesc(2u, BM, 2 * BN, 0u, 0u);
+                constexpr uint32_t idesc_cat = make_idesc(2u, BM, 2 * BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
                 umma_tf32(d_tmem, dah, dbh, idesc_cat, acc0);  // [hi.hi | hi.lo]: the descriptor at B_hi spans both planes
                 umma_tf32(d_tmem, dal, dbh, idesc, 1u);        // + lo.hi
               } else if (s.x3 == 1) {
@@ -603,7 +609,7 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
     if (s.a_mn) rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.M, (uint64_t)s.K, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, 32, 2, true);
     else rc3 = make_tmap_3d(&tA, A, TMAP_F32, (uint64_t)s.K, (uint64_t)s.M, 2, (uint64_t)lda * 4, s.plane_a * 4, 32, BM, 2);
     if (rc3) return rc3;
-    if (s.b_mn) rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.N, (uint64_t)s.K, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 32, 2, true);
+    if (s.b_mn) rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.N, (uint64_t)s.K, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, 32, 1, true);
     else rc3 = make_tmap_3d(&tB, B, TMAP_F32, (uint64_t)s.K, (uint64_t)s.N, 2, (uint64_t)ldb * 4, s.plane_b * 4, 32, bn3, 2);
     if (rc3) return rc3;
     if (bn3 == 128) {
