@@ -32,17 +32,26 @@ constexpr int ATT_BK = 128;
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 // smem layout (offsets from a 1024-aligned base)
-// Sized so that TWO CTAs are resident per SM (96 KB smem, 256 TMEM columns each): the softmax of one CTA overlaps
+// Sized so that TWO CTAs are resident per SM (<= 113 KB smem, 256 TMEM columns each): the softmax of one CTA overlaps
 // the tensor-core work of the other, which hides most of the exp/max latency a single softmax warpgroup exposes.
+// KST = K stages.  With ONE (round 1) the load of K_{j+1} can only be issued when QK_j has completed, and S_{j+1} cannot be
+// computed before it lands: the kernel ran at one TMA round trip (1.5-2 us under load) per key tile -- 4700 clk per tile
+// against ~2000 of softmax.  With TWO, K_{j+1} is requested a whole tile ahead.  The second stage only fits beside a
+// second resident CTA without the 1 KB alignment slack and without the PAIR-mode exchange buffer (2 x (112 KB + 1 KB) per SM).
 constexpr int ATT_OFF_Q = 0;
-constexpr int ATT_OFF_K = ATT_OFF_Q + ATT_TILE_BYTES;          // 1 stage (freed as soon as QK_j completes)
-constexpr int ATT_OFF_V = ATT_OFF_K + ATT_TILE_BYTES;          // 2 stages
-constexpr int ATT_OFF_P = ATT_OFF_V + 2 * ATT_TILE_BYTES;      // 1 buffer x 2 k-atoms x 16 KB
-constexpr int ATT_OFF_BAR = ATT_OFF_P + 2 * ATT_TILE_BYTES;
-constexpr int ATT_NUM_BARS = 1 + 1 + 1 + 2 + 2 + 1 + 1 + 1 + 2;
-constexpr int ATT_OFF_TMEM = ATT_OFF_BAR + ATT_NUM_BARS * 8;
-constexpr int ATT_OFF_XCH = ATT_OFF_TMEM + 16;                 // PAIR mode: row-max / row-sum exchange, [2 parity][2 half][128]
-constexpr int ATT_SMEM_TOTAL = ATT_OFF_XCH + 2 * 2 * 128 * 4 + 1024;
+constexpr int ATT_OFF_K = ATT_OFF_Q + ATT_TILE_BYTES;
+constexpr int ATT_NUM_BARS = 1 + 2 + 2 + 2 + 2 + 1 + 1 + 1 + 2;
+template <int KST, bool PAIR>
+struct AttSmem {
+  static constexpr int OFF_V = ATT_OFF_K + KST * ATT_TILE_BYTES;    // 2 stages
+  static constexpr int OFF_P = OFF_V + 2 * ATT_TILE_BYTES;          // 1 buffer x 2 k-atoms x 16 KB
+  static constexpr int OFF_BAR = OFF_P + 2 * ATT_TILE_BYTES;
+  static constexpr int OFF_TMEM = OFF_BAR + ATT_NUM_BARS * 8;
+  static constexpr int OFF_XCH = OFF_TMEM + 16;                     // PAIR mode: row-max / row-sum exchange, [2 parity][2 half][128]
+  static constexpr bool SLACK = KST == 1;                           // KST == 2: the dynamic smem base must be 1024-aligned (checked)
+  static constexpr int TOTAL = OFF_XCH + (PAIR ? 2 * 2 * 128 * 4 : 0) + (SLACK ? 1024 : 0);
+};
+static_assert(2 * (AttSmem<2, false>::TOTAL + 1024) <= 228 * 1024, "two CTAs with two K stages must fit one SM");
 // TMEM columns: S [0,128) O0 [128,192) O1 [192,256)
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t ATT_TM_S = 0, ATT_TM_O = 128;
@@ -72,7 +81,7 @@ __device__ __forceinline__ float ex2_fma(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));   // p * 2^n
 }
 
-template <int MODE>
+template <int MODE, int KST = 1>
 __global__ void __launch_bounds__(MODE == 2 ? 320 : ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int C,
                     float scale_log2e, float* __restrict__ lse) {
@@ -80,23 +89,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   constexpr bool PAIR = MODE == 2;
   constexpr bool POLY = MODE == 3;   // MODE 3 = MODE 1 with a quarter of the exponentials on the FMA pipe
   constexpr int NSOFT = PAIR ? 256 : 128;  // softmax threads
+  using L = AttSmem<KST, PAIR>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = L::SLACK ? reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023)) : smem_raw;
+  if (!L::SLACK && (smem_u32(smem_raw) & 1023u) != 0) dev_fail(0xA11Du, 0);  // swizzled TMA tiles need 1024-byte alignment
   uint8_t* sQ = smem + ATT_OFF_Q;
   uint8_t* sK = smem + ATT_OFF_K;
-  uint8_t* sV = smem + ATT_OFF_V;
-  uint8_t* sP = smem + ATT_OFF_P;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
+  uint8_t* sV = smem + L::OFF_V;
+  uint8_t* sP = smem + L::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 2;
-  uint64_t* v_full = bars + 3;   // [2]
-  uint64_t* v_empty = bars + 5;  // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* s_empty = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* o_full = bars + 10;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ATT_OFF_TMEM);
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_full = bars + 12;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,8 +119,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
-    mbar_init(k_full, 1);
-    mbar_init(k_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(s_empty, NSOFT);
     mbar_init(p_full, NSOFT);
@@ -139,9 +152,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        mbar_wait_relaxed(k_empty, (j & 1) ^ 1, 10);
-        mbar_expect_tx(k_full, ATT_TILE_BYTES);
-        tma_load_3d(sK, &tm_qkv, k_full, C + head * ATT_D, j * ATT_BK, b);
+        const int ks = j % KST;
+        mbar_wait_relaxed(&k_empty[ks], ((j / KST) & 1) ^ 1, 10);
+        mbar_expect_tx(&k_full[ks], ATT_TILE_BYTES);
+        tma_load_3d(sK + ks * ATT_TILE_BYTES, &tm_qkv, &k_full[ks], C + head * ATT_D, j * ATT_BK, b);
         mbar_wait_relaxed(&v_empty[st], ph ^ 1, 11);
         mbar_expect_tx(&v_full[st], ATT_TILE_BYTES);
         tma_load_3d(sV + st * ATT_TILE_BYTES, &tm_qkv, &v_full[st], 2 * C + head * ATT_D, j * ATT_BK, b);
@@ -154,15 +168,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       constexpr uint32_t idesc_o = make_idesc(1, 128, 64, 0, 1);   // P (K-major) x V (MN-major)
       auto issue_qk = [&](int j) {
         const uint32_t ph = j & 1;
-        mbar_wait(k_full, ph, 12);
+        const int ks = j % KST;
+        mbar_wait(&k_full[ks], (j / KST) & 1, 12);
         mbar_wait(s_empty, ph ^ 1, 13);
         tc_fence_after();
         const uint64_t da = make_smem_desc(smem_u32(sQ), 0, 1024, 2);
-        const uint64_t db = make_smem_desc(smem_u32(sK), 0, 1024, 2);
+        const uint64_t db = make_smem_desc(smem_u32(sK + ks * ATT_TILE_BYTES), 0, 1024, 2);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem_base + ATT_TM_S, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k > 0);
-        umma_commit(k_empty);
+        umma_commit(&k_empty[ks]);
         umma_commit(s_full);
       };
       mbar_wait(q_full, 0, 14);
@@ -196,7 +211,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     if constexpr (PAIR) {
       const int half = (warp - 2) >> 2;   // keys [half * 64, half * 64 + 64) of every tile; O columns [half * 32, +32)
-      float* xch = reinterpret_cast<float*>(smem + ATT_OFF_XCH);
+      float* xch = reinterpret_cast<float*>(smem + L::OFF_XCH);
       float m_run = -INFINITY, l_run = 0.f;  // l_run: this thread's half of the row sum
       for (int j = 0; j < T; ++j) {
         mbar_wait(s_full, j & 1, 17);
@@ -623,13 +638,24 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   static bool attr_set = false;  // (attention is never launched inside a stream capture)
   static int mode = 1;  // DVT_ATTN_MODE: 0 O in registers, 1 lazy rescaling (default), 2 lazy + two threads per row,
                         // 3 lazy + a quarter of the exponentials on the FMA pipe
+  static int kst = 1;   // DVT_ATTN_KSTAGES: K stages of modes 1 / 3 (1 = the round-1 kernel)  [2 pending GPU validation]
+  constexpr int T1 = AttSmem<1, false>::TOTAL, T1P = AttSmem<1, true>::TOTAL, T2 = AttSmem<2, false>::TOTAL;
   if (!attr_set) {
-    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
-    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
-    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
-    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1P));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2));
     const char* v = getenv("DVT_ATTN_MODE");
     if (v && v[0] >= '0' && v[0] <= '3') mode = v[0] - '0';
+    const char* k = getenv("DVT_ATTN_KSTAGES");
+    if (k && (k[0] == '1' || k[0] == '2')) kst = k[0] - '0';
+    if (kst == 2) {  // the second K stage must not cost the second resident CTA
+      int per_sm = 0;
+      DVT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attention_tc_kernel<1, 2>, ATT_THREADS, (size_t)T2));
+      if (per_sm < 2) kst = 1;
+    }
     attr_set = true;
   }
   DVT_REQUIRE(lse == nullptr || mode == 1, "attention: the log-sum-exp output is implemented by DVT_ATTN_MODE=1 (default)");
@@ -639,10 +665,13 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   if (rc) return rc;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
   const float sl2 = scale * 1.4426950408889634f;
-  if (mode == 3) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
-  else if (mode == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<2>, grid, dim3(320), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
-  else if (mode == 1) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<1>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
-  else DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<0>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_TOTAL, stream, tm, out, N, C, sl2, lse));
+  const dim3 blk(ATT_THREADS);
+  if (mode == 3 && kst == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3, 2>, grid, blk, (size_t)T2, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 3) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<2, 1>, grid, dim3(320), (size_t)T1P, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 1 && kst == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<1, 2>, grid, blk, (size_t)T2, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 1) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<1, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
+  else DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<0, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
   DVT_CUDA_OK(cudaGetLastError());
   count_launch();
   return DVT_OK;
