@@ -81,6 +81,11 @@ __device__ __forceinline__ float ex2_fma(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));   // p * 2^n
 }
 
+// Profiling aid (dvt_debug_set_timestamp_buffer with >= 16 + 8 * 16 slots): clock64 milestones of CTA (0, 0, 0), per key tile
+// j < 16 at slot 16 + 8 j + k -- softmax warp 2: 0 waiting for S_j, 1 S_j ready, 2 S_j in registers, 3 P_j computed,
+// 4 PV_{j-1} done, 5 P_j stored; MMA warp: 6 QK_{j+1} issued, 7 PV_j issued.
+__device__ unsigned long long* d_att_dbg = nullptr;
+
 template <int MODE, int KST = 1>
 __global__ void __launch_bounds__(MODE == 2 ? 320 : ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int N, int C,
@@ -115,6 +120,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int T = (N + ATT_BK - 1) / ATT_BK;  // key tiles
+  unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? d_att_dbg : nullptr;
+  auto stamp = [&](int j, int k) {
+    if (dbg && j < 16) dbg[16 + 8 * j + k] = (unsigned long long)clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -179,6 +188,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           umma_f16(tmem_base + ATT_TM_S, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k > 0);
         umma_commit(&k_empty[ks]);
         umma_commit(s_full);
+        stamp(j - 1, 6);
       };
       mbar_wait(q_full, 0, 14);
       issue_qk(0);
@@ -189,6 +199,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         mbar_wait(&v_full[st], ph, 15);
         mbar_wait(p_full, j & 1, 16);
         tc_fence_after();
+        stamp(j, 7);
         // P buffer: two K-atoms (keys 0-63, 64-127), each a [128 x 128B] swizzled tile
         const uint32_t p_base = smem_u32(sP);
         const uint32_t v_base = smem_u32(sV + st * ATT_TILE_BYTES);
@@ -325,14 +336,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
       float m_run = -INFINITY;  // the maximum (of s * scale_log2e) this row's P / O / l are currently relative to
       float l_run = 0.f;
       for (int j = 0; j < T; ++j) {
+        if (warp == 2) stamp(j, 0);
         mbar_wait(s_full, j & 1, 17);
         tc_fence_after();
+        if (warp == 2) stamp(j, 1);
         uint32_t sreg[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_32x32(lane_addr + ATT_TM_S + c * 32, sreg[c]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_empty);  // S_j lives in registers now: QK of tile j+1 may overwrite the TMEM buffer
+        if (warp == 2) stamp(j, 2);
         const int kbase = j * ATT_BK;
         const bool partial = kbase + ATT_BK > N;  // only the last tile can hold keys >= N
         // eight independent maxima (a single running maximum is a chain of 128 dependent FMNMX: ~500 cycles of exposed
@@ -383,10 +397,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           }
         }
         const float l_tile = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        if (warp == 2) stamp(j, 3);
         if (j > 0) {
           // PV_{j-1} must have completed before the P buffer is overwritten / O is rescaled
           mbar_wait(&o_full[0], (j - 1) & 1, 18);
           tc_fence_after();
+          if (warp == 2) stamp(j, 4);
           if (__any_sync(0xffffffffu, grow)) {  // rare after the first tiles; tcgen05.ld / st are warp-collective
             uint32_t o[2][32];
             tmem_ld_32x32(lane_addr + ATT_TM_O, o[0]);
@@ -413,6 +429,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         fence_async_smem();  // generic-proxy writes of P -> visible to tcgen05.mma
         tc_fence_before();
         mbar_arrive(p_full);
+        if (warp == 2) stamp(j, 5);
         l_run = l_run * alpha + l_tile;
         m_run = m_use;
       }
@@ -676,5 +693,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   count_launch();
   return DVT_OK;
 }
+
+void attention_set_debug_buffer(unsigned long long* p) { cudaMemcpyToSymbol(d_att_dbg, &p, sizeof(p)); }
 
 }  // namespace dvt

@@ -26,12 +26,13 @@ constexpr int KB_BYTES = 128;  // bytes of K per pipeline stage row (= one 128B 
 // (M = 2048), so narrower tiles mean more CTAs, half the MMA time per k-block and a one-chunk-per-warp epilogue.
 // The 128x256 bf16 tiles (HP-1) get 12 epilogue warps: their GELU / residual epilogues are ALU- and latency-bound.
 // The 128x128 x3 tiles keep three 64 KB stages: only four epilogue warps' transpose scratch fits beside them.
-constexpr int epi_warps(int bn, bool x3) { return (bn == 256 && !x3) ? 12 : (x3 && bn == 128) ? 4 : 8; }
+// (so does the experimental four-stage variant of the 128x64 x3 tile: DVT_GEMM_X3_STAGES=4)
+constexpr int epi_warps(int bn, bool x3, int stages) { return (bn == 256 && !x3) ? 12 : (x3 && (bn == 128 || stages == 4)) ? 4 : 8; }
 constexpr int SCR_PITCH = 36;  // floats; 16B-aligned rows, conflict-free for the access pattern below
 
 template <int BN, int STAGES, bool X3 = false>
 struct GemmSmem {
-  static constexpr int EW = epi_warps(BN, X3);
+  static constexpr int EW = epi_warps(BN, X3, STAGES);
   static constexpr int THREADS = 32 * (2 + EW);
   static constexpr int A_BYTES = BM * KB_BYTES * (X3 ? 2 : 1);  // x3: hi plane then lo plane
   static constexpr int B_BYTES = BN * KB_BYTES * (X3 ? 2 : 1);
@@ -543,6 +544,9 @@ int gemm_prepare() {
   if ((rc = prep_one<64, 3, true, false, false, true>())) return rc;
   if ((rc = prep_one<64, 3, true, false, true, true>())) return rc;
   if ((rc = prep_one<64, 3, true, true, true, true>())) return rc;
+  if ((rc = prep_one<64, 4, true, false, false, true>())) return rc;
+  if ((rc = prep_one<64, 4, true, false, true, true>())) return rc;
+  if ((rc = prep_one<64, 4, true, true, true, true>())) return rc;
   if ((rc = prep_one<128, 3, true, false, false, true>())) return rc;
   if ((rc = prep_one<128, 3, true, false, true, true>())) return rc;
   if ((rc = prep_one<128, 3, true, true, true, true>())) return rc;
@@ -616,6 +620,12 @@ int launch_gemm_tn(const void* A, int lda, const void* B, int ldb, TmapDtype dty
       if (s.a_mn) return launch_tc<128, 3, true, true, true, true>(tA, tB, s, epi, stream);
       if (s.b_mn) return launch_tc<128, 3, true, false, true, true>(tA, tB, s, epi, stream);
       return launch_tc<128, 3, true, false, false, true>(tA, tB, s, epi, stream);
+    }
+    static const bool four = [] { const char* e = getenv("DVT_GEMM_X3_STAGES"); return e && e[0] == '4'; }();
+    if (four) {  // experiment: a fourth 48 KB stage (and four epilogue warps) for the 128 x 64 tile
+      if (s.a_mn) return launch_tc<64, 4, true, true, true, true>(tA, tB, s, epi, stream);
+      if (s.b_mn) return launch_tc<64, 4, true, false, true, true>(tA, tB, s, epi, stream);
+      return launch_tc<64, 4, true, false, false, true>(tA, tB, s, epi, stream);
     }
     if (s.a_mn) return launch_tc<64, 3, true, true, true, true>(tA, tB, s, epi, stream);
     if (s.b_mn) return launch_tc<64, 3, true, false, true, true>(tA, tB, s, epi, stream);
