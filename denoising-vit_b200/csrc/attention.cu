@@ -121,8 +121,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   const int b = blockIdx.z;
   const int T = (N + ATT_BK - 1) / ATT_BK;  // key tiles
   unsigned long long* dbg = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? d_att_dbg : nullptr;
+  // (compiled in with -DDVT_ATTN_TIMELINE only -- DVT_NVCC_EXTRA=-DDVT_ATTN_TIMELINE bash csrc/build.sh: the stamps sit in
+  // the hot loop of the softmax warps)
   auto stamp = [&](int j, int k) {
+#ifdef DVT_ATTN_TIMELINE
     if (dbg && j < 16) dbg[16 + 8 * j + k] = (unsigned long long)clock64();
+#else
+    (void)j; (void)k; (void)dbg;
+#endif
   };
 
   if (warp == 0 && lane == 0) {
