@@ -55,6 +55,7 @@ static_assert(2 * (AttSmem<2, false>::TOTAL + 1024) <= 228 * 1024, "two CTAs wit
 // TMEM columns: S [0,128) O0 [128,192) O1 [192,256)
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t ATT_TM_S = 0, ATT_TM_O = 128;
+constexpr uint32_t ATT_TM_P = 192;   // MODE 5: P (bf16 pairs, 64 columns) as the TMEM A operand of P.V
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -84,6 +85,12 @@ __device__ __forceinline__ float ex2_fma(float x) {
 // Profiling aid (dvt_debug_set_timestamp_buffer with >= 16 + 8 * 16 slots): clock64 milestones of CTA (0, 0, 0), per key tile
 // j < 16 at slot 16 + 8 j + k -- softmax warp 2: 0 waiting for S_j, 1 S_j ready, 2 S_j in registers, 3 P_j computed,
 // 4 PV_{j-1} done, 5 P_j stored; MMA warp: 6 QK_{j+1} issued, 7 PV_j issued.
+// MODE 4 (round 2): MODE 1 with the per-element arithmetic in packed fp32 pairs (FFMA2 for s * scale - m, FADD2 for the
+// row sums): 3.0 instead of 4.0 issue slots per score (FMNMX3/2 + FFMA2/2 + MUFU + FADD2/2 + F2FP/2); the softmax warps
+// are issue / latency bound (profiles/r2z_attention_timeline.txt), not MUFU bound.
+// MODE 5: MODE 4 with P handed to the tensor core through TENSOR MEMORY (tcgen05.st into columns [192, 256), P.V issued
+// with the A operand from TMEM) instead of a swizzled shared-memory tile: no 32 KB st.shared per tile, no
+// fence.proxy.async, no shared-memory operand reads for A (the timeline charges ~570 clk per key tile to that hand-over).
 __device__ unsigned long long* d_att_dbg = nullptr;
 
 template <int MODE, int KST = 1>
@@ -93,6 +100,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   constexpr bool LAZY = MODE >= 1;
   constexpr bool PAIR = MODE == 2;
   constexpr bool POLY = MODE == 3;   // MODE 3 = MODE 1 with a quarter of the exponentials on the FMA pipe
+  constexpr bool PK = MODE >= 4;     // packed fp32 pairs in the exponent / row-sum arithmetic
+  constexpr bool PTM = MODE == 5;    // P through tensor memory
   constexpr int NSOFT = PAIR ? 256 : 128;  // softmax threads
   using L = AttSmem<KST, PAIR>;
   extern __shared__ uint8_t smem_raw[];
@@ -214,7 +223,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
           const uint64_t da = make_smem_desc(p_base + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 0, 1024, 2);
           // V tile rows are keys (K dim), 128 B each: 16 keys per MMA = 2048 B; 8-row groups 1024 B apart
           const uint64_t db = make_smem_desc(v_base + k * 2048, 0, 1024, 2);
-          if (LAZY) umma_f16(tmem_base + ATT_TM_O, da, db, idesc_o, (j > 0) || (k > 0));  // one O, all key tiles
+          if (PTM) umma_f16_ts(tmem_base + ATT_TM_O, tmem_base + ATT_TM_P + k * 8, db, idesc_o, (j > 0) || (k > 0));
+          else if (LAZY) umma_f16(tmem_base + ATT_TM_O, da, db, idesc_o, (j > 0) || (k > 0));  // one O, all key tiles
           else umma_f16(tmem_base + ATT_TM_O + st * 64, da, db, idesc_o, k > 0);
         }
         umma_commit(&v_empty[st]);
@@ -376,12 +386,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         const bool grow = m_new - m_run > 8.0f;     // (first tile: m_run = -inf)
         const float m_use = grow ? m_new : m_run;
         const float alpha = grow ? ex2(m_run - m_new) : 1.0f;  // 0 on the first tile
-        uint32_t packed[4][16];
+        uint32_t packed[2][32];              // keys [64 h, 64 h + 64) as bf16 pairs: packed[h][0..31]
         float ls[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial row sums (same reason as the maxima)
+        float2 ls2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // PK: (even key, odd key) partial sums
+        const float2 sc2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int nval = partial ? N - kbase - c * 32 : 32;
           if (nval >= 32) {
+            if constexpr (PK) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 x = ffma2(make_float2(__uint_as_float(sreg[c][2 * i]), __uint_as_float(sreg[c][2 * i + 1])), sc2, nm2);
+                const float2 pp = make_float2(ex2(x.x), ex2(x.y));
+                ls2[i & 3] = fadd2(ls2[i & 3], pp);
+                packed[c >> 1][(c & 1) * 16 + i] = pack_bf16x2(pp.x, pp.y);
+              }
+            } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float x0 = fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use);
@@ -389,7 +410,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
               const float p0 = ex2(x0);
               const float p1 = (POLY && (i & 1)) ? ex2_fma(x1) : ex2(x1);
               ls[i & 3] += p0 + p1;
-              packed[c][i] = pack_bf16x2(p0, p1);
+              packed[c >> 1][(c & 1) * 16 + i] = pack_bf16x2(p0, p1);
+            }
             }
           } else {  // tail of the last key tile: keys >= N contribute neither to P nor to the row sum
 #pragma unroll
@@ -398,11 +420,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
               if (2 * i < nval) p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
               if (2 * i + 1 < nval) p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
               ls[i & 3] += p0 + p1;
-              packed[c][i] = pack_bf16x2(p0, p1);
+              packed[c >> 1][(c & 1) * 16 + i] = pack_bf16x2(p0, p1);
             }
           }
         }
-        const float l_tile = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        float l_tile = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        if constexpr (PK) {
+          const float2 t = fadd2(fadd2(ls2[0], ls2[1]), fadd2(ls2[2], ls2[3]));
+          l_tile += t.x + t.y;
+        }
         if (warp == 2) stamp(j, 3);
         if (j > 0) {
           // PV_{j-1} must have completed before the P buffer is overwritten / O is rescaled
@@ -421,6 +447,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
             tmem_st_wait();
           }
         }
+        if constexpr (PTM) {
+          // row `row` of P = TMEM lane `row`; column 192 + c holds keys (2c, 2c + 1): the K-major A operand of P.V
+          tmem_st_32x32(lane_addr + ATT_TM_P, packed[0]);
+          tmem_st_32x32(lane_addr + ATT_TM_P + 32, packed[1]);
+          tmem_st_wait();
+        } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           // keys [c*32, c*32+32) -> k-atom (c >> 1), 16B chunks ((c & 1) * 4 + q), q = 0..3
@@ -428,11 +460,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
+            const int o = (c & 1) * 16 + 4 * q;
             *reinterpret_cast<uint4*>(atom + chunk * 16) =
-                make_uint4(packed[c][4 * q], packed[c][4 * q + 1], packed[c][4 * q + 2], packed[c][4 * q + 3]);
+                make_uint4(packed[c >> 1][o], packed[c >> 1][o + 1], packed[c >> 1][o + 2], packed[c >> 1][o + 3]);
           }
         }
         fence_async_smem();  // generic-proxy writes of P -> visible to tcgen05.mma
+        }
         tc_fence_before();
         mbar_arrive(p_full);
         if (warp == 2) stamp(j, 5);
@@ -670,8 +704,10 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1P));
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
     const char* v = getenv("DVT_ATTN_MODE");
-    if (v && v[0] >= '0' && v[0] <= '3') mode = v[0] - '0';
+    if (v && v[0] >= '0' && v[0] <= '5') mode = v[0] - '0';
     const char* k = getenv("DVT_ATTN_KSTAGES");
     if (k && (k[0] == '1' || k[0] == '2')) kst = k[0] - '0';
     if (kst == 2) {  // the second K stage must not cost the second resident CTA
@@ -681,7 +717,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     }
     attr_set = true;
   }
-  DVT_REQUIRE(lse == nullptr || mode == 1, "attention: the log-sum-exp output is implemented by DVT_ATTN_MODE=1 (default)");
+  DVT_REQUIRE(lse == nullptr || mode == 1 || mode >= 4, "attention: the log-sum-exp output is implemented by DVT_ATTN_MODE=1, 4, 5");
   CUtensorMap tm;
   int rc = make_tmap_3d(&tm, qkv, TMAP_BF16, (uint64_t)3 * C, (uint64_t)N, (uint64_t)B, (uint64_t)3 * C * 2,
                         (uint64_t)N * 3 * C * 2, ATT_D, ATT_BK);
@@ -689,7 +725,9 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
   const float sl2 = scale * 1.4426950408889634f;
   const dim3 blk(ATT_THREADS);
-  if (mode == 3 && kst == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3, 2>, grid, blk, (size_t)T2, stream, tm, out, N, C, sl2, lse));
+  if (mode == 5) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<5, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 4) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<4, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 3 && kst == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3, 2>, grid, blk, (size_t)T2, stream, tm, out, N, C, sl2, lse));
   else if (mode == 3) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
   else if (mode == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<2, 1>, grid, dim3(320), (size_t)T1P, stream, tm, out, N, C, sl2, lse));
   else if (mode == 1 && kst == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<1, 2>, grid, blk, (size_t)T2, stream, tm, out, N, C, sl2, lse));
