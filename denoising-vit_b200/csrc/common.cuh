@@ -424,6 +424,24 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-a, e, fmaxf(x, 0.0f));
 }
 
+// Two GELUs in packed fp32 pairs: the polynomial is evaluated in n = -min(|x|, 8.485) (one FMNMX with source modifiers; the
+// odd coefficients change sign, every intermediate is the exact negation or copy of the scalar form's, so the result is
+// bit-identical to gelu_erf), 7 FFMA2 + 2 FMNMX + 2 FMNMX + 2 MUFU per pair: 6.5 instead of 10 issue slots per element.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 n = make_float2(fmaxf(-fabsf(x.x), -8.485281374f), fmaxf(-fabsf(x.y), -8.485281374f));
+  float2 q = make_float2(1.9755745359180961e-05f, 1.9755745359180961e-05f);
+  q = ffma2(q, n, make_float2(6.6162906245512902e-04f, 6.6162906245512902e-04f));
+  q = ffma2(q, n, make_float2(7.7581320540732555e-03f, 7.7581320540732555e-03f));
+  q = ffma2(q, n, make_float2(5.2962877549126521e-02f, 5.2962877549126521e-02f));
+  q = ffma2(q, n, make_float2(-4.5906686494096666e-01f, -4.5906686494096666e-01f));
+  q = ffma2(q, n, make_float2(1.1511190142292334f, 1.1511190142292334f));
+  q = ffma2(q, n, make_float2(-1.0f, -1.0f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  return ffma2(n, e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+
 // d/dx gelu_erf(x) = Phi(x) + x phi(x)
 __device__ __forceinline__ float gelu_grad(float x) {
   return fmaf(x * 0.3989422804014327f, __expf(-0.5f * x * x), 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f)));

@@ -106,19 +106,32 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
           const int m = m0 + 4 * jj;
           float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
           uint2 pk;
-          pk.x = pack_bf16x2(gelu_erf(x.x + b4.x), gelu_erf(x.y + b4.y));
-          pk.y = pack_bf16x2(gelu_erf(x.z + b4.z), gelu_erf(x.w + b4.w));
+          const float2 g01 = gelu_erf2(fadd2(make_float2(x.x, x.y), make_float2(b4.x, b4.y)));
+          const float2 g23 = gelu_erf2(fadd2(make_float2(x.z, x.w), make_float2(b4.z, b4.w)));
+          pk.x = pack_bf16x2(g01.x, g01.y);
+          pk.y = pack_bf16x2(g23.x, g23.y);
           if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
         }
-      } else {
-        const float lo = e.act == ACT_RELU ? 0.0f : -INFINITY;
+      } else if (e.act == ACT_RELU) {
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int m = m0 + 4 * jj;
           float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
           uint2 pk;
-          pk.x = pack_bf16x2(fmaxf(x.x + b4.x, lo), fmaxf(x.y + b4.y, lo));
-          pk.y = pack_bf16x2(fmaxf(x.z + b4.z, lo), fmaxf(x.w + b4.w, lo));
+          pk.x = pack_bf16x2(fmaxf(x.x + b4.x, 0.0f), fmaxf(x.y + b4.y, 0.0f));
+          pk.y = pack_bf16x2(fmaxf(x.z + b4.z, 0.0f), fmaxf(x.w + b4.w, 0.0f));
+          if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
+        }
+      } else {   // bias only (QKV): two FADD2 and two packs per four outputs
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int m = m0 + 4 * jj;
+          float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+          const float2 v01 = fadd2(make_float2(x.x, x.y), make_float2(b4.x, b4.y));
+          const float2 v23 = fadd2(make_float2(x.z, x.w), make_float2(b4.z, b4.w));
+          uint2 pk;
+          pk.x = pack_bf16x2(v01.x, v01.y);
+          pk.y = pack_bf16x2(v23.x, v23.y);
           if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
         }
       }
@@ -129,10 +142,11 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
       for (int jj = 0; jj < 8; ++jj) {
         const int m = m0 + 4 * jj;
         const float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
-        float4 o = xin[jj];
-        o.x = fmaf(g4.x, x.x + b4.x, o.x); o.y = fmaf(g4.y, x.y + b4.y, o.y);
-        o.z = fmaf(g4.z, x.z + b4.z, o.z); o.w = fmaf(g4.w, x.w + b4.w, o.w);
-        if (m < s.M) *reinterpret_cast<float4*>(outp + (size_t)m * e.ldo + n) = o;
+        const float2 o01 = ffma2(make_float2(g4.x, g4.y), fadd2(make_float2(x.x, x.y), make_float2(b4.x, b4.y)),
+                                 make_float2(xin[jj].x, xin[jj].y));
+        const float2 o23 = ffma2(make_float2(g4.z, g4.w), fadd2(make_float2(x.z, x.w), make_float2(b4.z, b4.w)),
+                                 make_float2(xin[jj].z, xin[jj].w));
+        if (m < s.M) *reinterpret_cast<float4*>(outp + (size_t)m * e.ldo + n) = make_float4(o01.x, o01.y, o23.x, o23.y);
       }
     } else {
       // ---- generic path (fit epilogues: masks, split planes, atomics, remap) ----
