@@ -91,6 +91,10 @@ __device__ __forceinline__ float ex2_fma(float x) {
 // MODE 5: MODE 4 with P handed to the tensor core through TENSOR MEMORY (tcgen05.st into columns [192, 256), P.V issued
 // with the A operand from TMEM) instead of a swizzled shared-memory tile: no 32 KB st.shared per tile, no
 // fence.proxy.async, no shared-memory operand reads for A (the timeline charges ~570 clk per key tile to that hand-over).
+// MODE 6: MODE 4 with each 32-key chunk of P stored to shared memory as soon as it is packed (the stores drain under the
+// remaining exponentials, the proxy fence at the end only has the last chunk to wait for, 48 fewer live registers), and the
+// wait for PV_{j-1} (P buffer free) moved in front of the exponentials -- by then PV_{j-1} has had the S load and the
+// row-max pass to finish.  The rare rescaling of O stays behind the exponentials (it needs 64 registers).
 __device__ unsigned long long* d_att_dbg = nullptr;
 
 template <int MODE, int KST = 1>
@@ -101,6 +105,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
   constexpr bool PAIR = MODE == 2;
   constexpr bool POLY = MODE == 3;   // MODE 3 = MODE 1 with a quarter of the exponentials on the FMA pipe
   constexpr bool PK = MODE >= 4;     // packed fp32 pairs in the exponent / row-sum arithmetic
+  constexpr bool EARLY = MODE == 6;  // P stored chunk by chunk under the exponentials, PV_{j-1} awaited before them
   constexpr bool PTM = MODE == 5;    // P through tensor memory
   constexpr int NSOFT = PAIR ? 256 : 128;  // softmax threads
   using L = AttSmem<KST, PAIR>;
@@ -386,7 +391,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         const bool grow = m_new - m_run > 8.0f;     // (first tile: m_run = -inf)
         const float m_use = grow ? m_new : m_run;
         const float alpha = grow ? ex2(m_run - m_new) : 1.0f;  // 0 on the first tile
-        uint32_t packed[2][32];              // keys [64 h, 64 h + 64) as bf16 pairs: packed[h][0..31]
+        auto wait_pv = [&]() {
+          // PV_{j-1} must have completed before the P buffer is overwritten / O is rescaled
+          mbar_wait(&o_full[0], (j - 1) & 1, 18);
+          tc_fence_after();
+          if (warp == 2) stamp(j, 4);
+        };
+        auto store_p_chunk = [&](int c, const uint32_t (&pk)[16]) {
+          // keys [c*32, c*32+32) -> k-atom (c >> 1), 16B chunks ((c & 1) * 4 + q), q = 0..3
+          uint8_t* atom = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
+            *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+        };
+        if constexpr (EARLY) {
+          if (j > 0) wait_pv();
+        }
+        uint32_t packed[4][16];              // keys [32 c, 32 c + 32) as bf16 pairs
         float ls[4] = {0.f, 0.f, 0.f, 0.f};  // four independent partial row sums (same reason as the maxima)
         float2 ls2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};  // PK: (even key, odd key) partial sums
         const float2 sc2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-m_use, -m_use);
@@ -400,7 +423,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
                 const float2 x = ffma2(make_float2(__uint_as_float(sreg[c][2 * i]), __uint_as_float(sreg[c][2 * i + 1])), sc2, nm2);
                 const float2 pp = make_float2(ex2(x.x), ex2(x.y));
                 ls2[i & 3] = fadd2(ls2[i & 3], pp);
-                packed[c >> 1][(c & 1) * 16 + i] = pack_bf16x2(pp.x, pp.y);
+                packed[c][i] = pack_bf16x2(pp.x, pp.y);
               }
             } else {
 #pragma unroll
@@ -410,7 +433,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
               const float p0 = ex2(x0);
               const float p1 = (POLY && (i & 1)) ? ex2_fma(x1) : ex2(x1);
               ls[i & 3] += p0 + p1;
-              packed[c >> 1][(c & 1) * 16 + i] = pack_bf16x2(p0, p1);
+              packed[c][i] = pack_bf16x2(p0, p1);
             }
             }
           } else {  // tail of the last key tile: keys >= N contribute neither to P nor to the row sum
@@ -420,9 +443,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
               if (2 * i < nval) p0 = ex2(fmaf(__uint_as_float(sreg[c][2 * i]), scale_log2e, -m_use));
               if (2 * i + 1 < nval) p1 = ex2(fmaf(__uint_as_float(sreg[c][2 * i + 1]), scale_log2e, -m_use));
               ls[i & 3] += p0 + p1;
-              packed[c >> 1][(c & 1) * 16 + i] = pack_bf16x2(p0, p1);
+              packed[c][i] = pack_bf16x2(p0, p1);
             }
           }
+          if constexpr (EARLY) store_p_chunk(c, packed[c]);
         }
         float l_tile = (ls[0] + ls[1]) + (ls[2] + ls[3]);
         if constexpr (PK) {
@@ -431,10 +455,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         }
         if (warp == 2) stamp(j, 3);
         if (j > 0) {
-          // PV_{j-1} must have completed before the P buffer is overwritten / O is rescaled
-          mbar_wait(&o_full[0], (j - 1) & 1, 18);
-          tc_fence_after();
-          if (warp == 2) stamp(j, 4);
+          if constexpr (!EARLY) wait_pv();
           if (__any_sync(0xffffffffu, grow)) {  // rare after the first tiles; tcgen05.ld / st are warp-collective
             uint32_t o[2][32];
             tmem_ld_32x32(lane_addr + ATT_TM_O, o[0]);
@@ -449,21 +470,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* _
         }
         if constexpr (PTM) {
           // row `row` of P = TMEM lane `row`; column 192 + c holds keys (2c, 2c + 1): the K-major A operand of P.V
-          tmem_st_32x32(lane_addr + ATT_TM_P, packed[0]);
-          tmem_st_32x32(lane_addr + ATT_TM_P + 32, packed[1]);
+          uint32_t h0[32], h1[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            h0[i] = packed[0][i]; h0[16 + i] = packed[1][i];
+            h1[i] = packed[2][i]; h1[16 + i] = packed[3][i];
+          }
+          tmem_st_32x32(lane_addr + ATT_TM_P, h0);
+          tmem_st_32x32(lane_addr + ATT_TM_P + 32, h1);
           tmem_st_wait();
         } else {
+        if constexpr (!EARLY) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // keys [c*32, c*32+32) -> k-atom (c >> 1), 16B chunks ((c & 1) * 4 + q), q = 0..3
-          uint8_t* atom = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
-            const int o = (c & 1) * 16 + 4 * q;
-            *reinterpret_cast<uint4*>(atom + chunk * 16) =
-                make_uint4(packed[c >> 1][o], packed[c >> 1][o + 1], packed[c >> 1][o + 2], packed[c >> 1][o + 3]);
-          }
+          for (int c = 0; c < 4; ++c) store_p_chunk(c, packed[c]);
         }
         fence_async_smem();  // generic-proxy writes of P -> visible to tcgen05.mma
         }
@@ -693,8 +712,9 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     return DVT_OK;
   }
   static bool attr_set = false;  // (attention is never launched inside a stream capture)
-  static int mode = 1;  // DVT_ATTN_MODE: 0 O in registers, 1 lazy rescaling (default), 2 lazy + two threads per row,
-                        // 3 lazy + a quarter of the exponentials on the FMA pipe
+  static int mode = 4;  // DVT_ATTN_MODE: 0 O in registers, 1 lazy rescaling, 2 lazy + two threads per row, 3 lazy + a quarter
+                        // of the exponentials on the FMA pipe, 4 (default) lazy + packed fp32 pairs, 5 = 4 + P through TMEM,
+                        // 6 = 4 + P stored chunk by chunk under the exponentials
   static int kst = 1;   // DVT_ATTN_KSTAGES: K stages of modes 1 / 3 (1 = the round-1 kernel)  [2 pending GPU validation]
   constexpr int T1 = AttSmem<1, false>::TOTAL, T1P = AttSmem<1, true>::TOTAL, T2 = AttSmem<2, false>::TOTAL;
   if (!attr_set) {
@@ -706,8 +726,9 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2));
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
+    DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
     const char* v = getenv("DVT_ATTN_MODE");
-    if (v && v[0] >= '0' && v[0] <= '5') mode = v[0] - '0';
+    if (v && v[0] >= '0' && v[0] <= '6') mode = v[0] - '0';
     const char* k = getenv("DVT_ATTN_KSTAGES");
     if (k && (k[0] == '1' || k[0] == '2')) kst = k[0] - '0';
     if (kst == 2) {  // the second K stage must not cost the second resident CTA
@@ -725,7 +746,8 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, B);
   const float sl2 = scale * 1.4426950408889634f;
   const dim3 blk(ATT_THREADS);
-  if (mode == 5) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<5, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
+  if (mode == 6) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<6, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
+  else if (mode == 5) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<5, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
   else if (mode == 4) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<4, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
   else if (mode == 3 && kst == 2) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3, 2>, grid, blk, (size_t)T2, stream, tm, out, N, C, sl2, lse));
   else if (mode == 3) DVT_CUDA_OK(launch_k(g_vit_pdl, attention_tc_kernel<3, 1>, grid, blk, (size_t)T1, stream, tm, out, N, C, sl2, lse));
