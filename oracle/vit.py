@@ -11,11 +11,13 @@ restatements the reference itself carries are followed where they exist:
   * block order, ls1/ls2 -> evaluation/vitdet/vision_transformer.py:98-117
   * pos-embed handling   -> evaluation/vitdet/vision_transformer.py:120-138
 
-PINNING: the reference has no tests or golden vectors for this path.  This restatement is
-pinned against an independent implementation of the same architecture, `transformers.Dinov2Model`
-(tests/golden/make_vit_golden.py -> tests/golden/vit_*.npz, checked by tests/test_oracle_vit.py).  The
-pos-embed *resampling* branch (grid != native) has no second implementation available offline:
-"parity unpinned" for that branch only.
+PINNING: the reference has no tests or golden vectors for this path.  This restatement is pinned
+(i) against the reference's OWN code for attention, block order / LayerScale / residuals and the pos-embed add --
+evaluation/vitdet/vision_transformer.py:69-138 executed on torch layers (tests/golden/make_vit_block_golden.py ->
+tests/golden/vit_ref_block.npz, both attention branches) -- and (ii) end to end against an independent implementation of the
+same architecture, `transformers.Dinov2Model` (tests/golden/make_vit_golden.py -> tests/golden/vit_hf_*.npz); both are
+checked by tests/test_oracle_vit.py.  The pos-embed *resampling* branch (grid != native) has no second implementation
+available offline: "parity unpinned" for that branch only.
 """
 from __future__ import annotations
 

@@ -45,3 +45,26 @@ def test_reshape_and_stride_contract():
     a = O.forward_intermediates(sd, cfg, x, [0])[0]
     b = O.forward_intermediates(sd, cfg, x, [0, 1])[0]
     assert torch.equal(a, b)
+
+
+def test_oracle_block_matches_reference_vitdet_code():
+    """oracle/vit.py attention / block / pos-embed add against outputs of the reference's OWN code for them
+    (evaluation/vitdet/vision_transformer.py:69-138, executed by tests/golden/make_vit_block_golden.py on torch layers with
+    timm's attribute names): written-out softmax branch, SDPA branch, LayerScale, residual order."""
+    z = np.load(os.path.join(GOLD, "vit_ref_block.npz"))
+    dim, heads, hidden, B, H, W = [int(v) for v in z["meta"]]
+    cfg = O.ViTConfig(embed_dim=dim, depth=1, num_heads=heads, patch_size=14, native_img=14 * H, mlp_hidden=hidden)
+    sd = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    x = torch.from_numpy(z["x"]).reshape(B, H * W, dim)
+    got = O.block(x, sd, 0, cfg).reshape(B, H, W, dim)
+    for key in ("y_block", "y_block_sdpa"):
+        ref = torch.from_numpy(z[key])
+        assert torch.allclose(got, ref, atol=5e-6, rtol=1e-5), (key, (got - ref).abs().max())
+    p = "blocks.0."
+    xn = torch.nn.functional.layer_norm(x, (dim,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], cfg.ln_eps)
+    att = O.attention(xn, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"], sd[p + "attn.proj.weight"],
+                      sd[p + "attn.proj.bias"], heads).reshape(B, H, W, dim)
+    assert torch.allclose(att, torch.from_numpy(z["y_attn"]), atol=5e-6, rtol=1e-5)
+    # pos-embed of the patch tokens on the stored grid (vision_transformer.py:120-138): prefix position dropped, added as is
+    pos = O.resample_abs_pos_embed(torch.from_numpy(z["pos_embed"]), (H, W), (H, W), 1)
+    assert torch.equal(x + pos[:, 1:], torch.from_numpy(z["y_pos"]).reshape(B, H * W, dim))
