@@ -101,29 +101,16 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
       // branch-free (QKV and fc1+GELU, the two largest epilogues of the ViT forward).
       __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.out);
       if (e.act == ACT_GELU) {
-        // Four rows are read from the scratch tile BEFORE the first global store of the group: `scr` is a generic pointer,
-        // so the compiler must otherwise order every scratch load behind the previous row's store (possible alias) and
-        // the row chains -- load, bias, GELU polynomial, exp2, pack, store: ~100 cycles of dependent latency each -- run
-        // one after the other instead of interleaved (eight independent pair chains per group now).
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float4 xr[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            xr[k] = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * (4 * g + k)) * SCR_PITCH + col4);
-          uint2 pk[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 g01 = gelu_erf2(fadd2(make_float2(xr[k].x, xr[k].y), make_float2(b4.x, b4.y)));
-            const float2 g23 = gelu_erf2(fadd2(make_float2(xr[k].z, xr[k].w), make_float2(b4.z, b4.w)));
-            pk[k].x = pack_bf16x2(g01.x, g01.y);
-            pk[k].y = pack_bf16x2(g23.x, g23.y);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int m = m0 + 4 * (4 * g + k);
-            if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk[k];
-          }
+        for (int jj = 0; jj < 8; ++jj) {
+          const int m = m0 + 4 * jj;
+          float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+          uint2 pk;
+          const float2 g01 = gelu_erf2(fadd2(make_float2(x.x, x.y), make_float2(b4.x, b4.y)));
+          const float2 g23 = gelu_erf2(fadd2(make_float2(x.z, x.w), make_float2(b4.z, b4.w)));
+          pk.x = pack_bf16x2(g01.x, g01.y);
+          pk.y = pack_bf16x2(g23.x, g23.y);
+          if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
         }
       } else if (e.act == ACT_RELU) {
 #pragma unroll
@@ -135,20 +122,17 @@ __device__ __forceinline__ void epi_chunk(const GemmEpi& e, const GemmShape& s, 
           pk.y = pack_bf16x2(fmaxf(x.z + b4.z, 0.0f), fmaxf(x.w + b4.w, 0.0f));
           if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
         }
-      } else {   // bias only (QKV): two FADD2 and two packs per four outputs; scratch reads before the stores (as above)
-        uint2 pk[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
-          const float2 v01 = fadd2(make_float2(x.x, x.y), make_float2(b4.x, b4.y));
-          const float2 v23 = fadd2(make_float2(x.z, x.w), make_float2(b4.z, b4.w));
-          pk[jj].x = pack_bf16x2(v01.x, v01.y);
-          pk[jj].y = pack_bf16x2(v23.x, v23.y);
-        }
+      } else {   // bias only (QKV): two FADD2 and two packs per four outputs
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int m = m0 + 4 * jj;
-          if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk[jj];
+          float4 x = *reinterpret_cast<const float4*>(scr + ((lane >> 3) + 4 * jj) * SCR_PITCH + col4);
+          const float2 v01 = fadd2(make_float2(x.x, x.y), make_float2(b4.x, b4.y));
+          const float2 v23 = fadd2(make_float2(x.z, x.w), make_float2(b4.z, b4.w));
+          uint2 pk;
+          pk.x = pack_bf16x2(v01.x, v01.y);
+          pk.y = pack_bf16x2(v23.x, v23.y);
+          if (m < s.M) *reinterpret_cast<uint2*>(outp + (size_t)m * e.ldo + n) = pk;
         }
       }
     } else if (!FIT && plain && e.out_mode == OUT_F32_RESID && e.act == ACT_NONE) {
