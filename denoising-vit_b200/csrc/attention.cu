@@ -87,14 +87,16 @@ __device__ __forceinline__ float ex2_fma(float x) {
 // 4 PV_{j-1} done, 5 P_j stored; MMA warp: 6 QK_{j+1} issued, 7 PV_j issued.
 // MODE 4 (round 2): MODE 1 with the per-element arithmetic in packed fp32 pairs (FFMA2 for s * scale - m, FADD2 for the
 // row sums): 3.0 instead of 4.0 issue slots per score (FMNMX3/2 + FFMA2/2 + MUFU + FADD2/2 + F2FP/2); the softmax warps
-// are issue / latency bound (profiles/r2z_attention_timeline.txt), not MUFU bound.
+// are issue / latency bound (profiles/r2z_attention_timeline.txt), not MUFU bound.  Measured 0.366 -> 0.352 ms (default).
 // MODE 5: MODE 4 with P handed to the tensor core through TENSOR MEMORY (tcgen05.st into columns [192, 256), P.V issued
 // with the A operand from TMEM) instead of a swizzled shared-memory tile: no 32 KB st.shared per tile, no
 // fence.proxy.async, no shared-memory operand reads for A (the timeline charges ~570 clk per key tile to that hand-over).
+// Parity-green, measured SLOWER (0.416 ms, profiles/r2z10_attention_epilogue_ab.txt): kept as a tested experiment.
 // MODE 6: MODE 4 with each 32-key chunk of P stored to shared memory as soon as it is packed (the stores drain under the
 // remaining exponentials, the proxy fence at the end only has the last chunk to wait for, 48 fewer live registers), and the
 // wait for PV_{j-1} (P buffer free) moved in front of the exponentials -- by then PV_{j-1} has had the S load and the
 // row-max pass to finish.  The rare rescaling of O stays behind the exponentials (it needs 64 registers).
+// Parity-green, measured 0.364 ms against 0.352 ms of MODE 4 (profiles/r2z11_validate.txt): not adopted.
 __device__ unsigned long long* d_att_dbg = nullptr;
 
 template <int MODE, int KST = 1>
@@ -715,7 +717,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int N,
   static int mode = 4;  // DVT_ATTN_MODE: 0 O in registers, 1 lazy rescaling, 2 lazy + two threads per row, 3 lazy + a quarter
                         // of the exponentials on the FMA pipe, 4 (default) lazy + packed fp32 pairs, 5 = 4 + P through TMEM,
                         // 6 = 4 + P stored chunk by chunk under the exponentials
-  static int kst = 1;   // DVT_ATTN_KSTAGES: K stages of modes 1 / 3 (1 = the round-1 kernel)  [2 pending GPU validation]
+  static int kst = 1;   // DVT_ATTN_KSTAGES: K stages of modes 1 / 3 (1 = the round-1 kernel)  [2: validated, measured neutral]
   constexpr int T1 = AttSmem<1, false>::TOTAL, T1P = AttSmem<1, true>::TOTAL, T2 = AttSmem<2, false>::TOTAL;
   if (!attr_set) {
     DVT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1));
