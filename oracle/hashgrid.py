@@ -16,6 +16,12 @@ grid_index, coherent-prime hash, pos_fract, kernel_grid) is restated here:
               (cx * 1) xor (cy * 2654435761)  (uint32)  otherwise (hashed)      then  % size_l
     out[:, l*F:(l+1)*F] = sum over the 4 corners of weight * table[offset_l + index]
 
+Known residual difference to a real tcnn run: tcnn evaluates `grid_scale` with the DEVICE exp2f inside its kernels (CUDA
+exp2f: up to 2 ulp) and with the host libm for the offset table; this restatement (and the CUDA path, which reads the scale
+from the same host-computed table) uses the correctly rounded host value for both.  A 1-2 ulp difference of scale_l moves
+`pos` by <= 2^-22 relative: interpolation weights change by ~1e-6, and a coordinate lands in the neighbouring cell only
+when it sits within that distance of a cell boundary.
+
 PARITY UNPINNED: tiny-cuda-nn cannot be imported here and the reference holds no golden vectors for it
 (SURVEY.md section 8c).  What IS pinned is the CUDA path against this restatement (bit-exact indices and
 interpolation weights, tests/test_fit_gpu.py) and the level table printed in SURVEY.md section 8a-5.
