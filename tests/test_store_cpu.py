@@ -179,3 +179,25 @@ def test_feature_store_dataset_reads_pairs_and_skips_missing(tmp_path):
         item = ds[i]
         assert np.array_equal(item["original_feats"], raw.numpy()) and item["denoised_feats"].shape == (h, w, C)
         assert "image" not in item
+
+
+def test_cli_flags_match_the_reference():
+    """Drop-in boundary: both stage CLIs accept every flag of the reference's parsers with the same type,
+    default, action, nargs and choices (golden: tests/golden/make_cli_golden.py reads the reference sources with ast)."""
+    import ast
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    try:
+        from make_cli_golden import KEYS, flags
+    finally:
+        sys.path.pop(0)
+    assert KEYS and ast
+    with open(os.path.join(root, "tests", "golden", "cli_flags.json")) as fh:
+        gold = json.load(fh)
+    for cli, ref in gold.items():
+        ours = flags(os.path.join(root, cli))
+        assert len(ref) >= 20
+        for name, spec in ref.items():
+            assert name in ours, f"{cli}: flag {name} of the reference is missing"
+            assert ours[name] == spec, f"{cli} {name}: {ours[name]} != reference {spec}"
