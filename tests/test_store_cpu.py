@@ -201,3 +201,25 @@ def test_cli_flags_match_the_reference():
         for name, spec in ref.items():
             assert name in ours, f"{cli}: flag {name} of the reference is missing"
             assert ours[name] == spec, f"{cli} {name}: {ours[name]} != reference {spec}"
+
+
+def test_model_api_signatures_match_the_reference():
+    """Drop-in boundary: `dvt.models` mirrors the reference's classes -- same public methods, same positional
+    parameters in the same order with the same defaults, same MODEL_LIST (extra keyword-only parameters are allowed)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    try:
+        from make_cli_golden import signatures
+    finally:
+        sys.path.pop(0)
+    with open(os.path.join(root, "tests", "golden", "api_signatures.json")) as fh:
+        gold = json.load(fh)
+    n = 0
+    for fname, ref in gold.items():
+        ours = signatures(os.path.join(root, "denoising-vit_b200", "dvt", "models", fname))
+        for name, spec in ref.items():
+            assert name in ours, f"{fname}: {name} of the reference is missing"
+            assert ours[name] == spec, f"{fname} {name}: {ours[name]} != reference {spec}"
+            n += 1
+    assert n >= 16
